@@ -1,0 +1,89 @@
+/* mobocmf_b200 — C ABI of the B200-native MFDGP hot path (sm_100a).
+ *
+ * The reference (fernandezdaniel/MOBOCMF) has no FFI: its boundary is the Python class API.  These
+ * entry points are what a binding for that path would call; each cites the reference code it replaces.  All
+ * pointers are DEVICE pointers to fp64 unless stated; sizes are explicit; `stream` is a cudaStream_t passed as
+ * void*.  Every function returns 0 on success, -1 on a CUDA launch error, -2 on an unsupported shape
+ * (M > 256, d > 8).  No function synchronises, allocates or keeps global state; scratch is caller-provided.
+ *
+ * Conventions
+ *   kind 0  layer-0 covariance  a * RBF_ARD(x)                       (mobocmf/layers/mfdgp_hidden_layer.py:43-47)
+ *           theta = [a, l_0 .. l_{d-1}]
+ *   kind 1  layer>=1 covariance k_x1 * (k_lin + k_f) + k_x2 on [x, f] (mobocmf/layers/mfdgp_hidden_layer.py:70-88,115)
+ *           theta = [a1, v_lin, a_f, l_f, a2, l1_0 .. l1_{d-1}, l2_0 .. l2_{d-1}]
+ *   theta holds CONSTRAINED values (softplus already applied); d = number of x columns (without f).
+ *   MP = M rounded up to a multiple of 32.  An "operator buffer" is mobo_ops_doubles(M) doubles laid out as
+ *   [L | W | WT | H | HT | P | LQ] (seven MP x MP row-major blocks), beta[MP], alpha[MP], scal[16]
+ *   (scal[0] = KL, scal[5] = Cholesky status: 0 ok, 1 not positive definite).
+ *   The GRADIENT of an operator buffer uses the same layout and, by convention, carries only
+ *   block W: A2 = sum_r dvar_r k_r k_r^T, block H: the same sum over clamped rows, alpha: sum_r dmu_r k_r,
+ *   scal[0]: d loss / d KL.
+ */
+#ifndef MOBOCMF_B200_H
+#define MOBOCMF_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* library / build identification: returns 100 for sm_100a */
+int mobo_abi_version(void);
+
+int mobo_padded_m(int M);
+size_t mobo_ops_doubles(int M);
+/* doubles needed for each of Ksave / Tsave / Usave of mobo_layer_rows_fwd for R rows */
+size_t mobo_rows_save_doubles(int M, long long R);
+/* scratch doubles for mobo_layer_rows_bwd / mobo_layer_precompute_bwd */
+size_t mobo_rows_bwd_work_doubles(int M, long long R);
+size_t mobo_precompute_bwd_work_doubles(int M);
+
+/* Per-step operators of one sparse-GP layer.
+ * Replaces: UnwhitenedVariationalStrategy.forward's K_zz + jitter, Cholesky and solves, and kl_mvn_mvn
+ * [upstream gpytorch], reached from mobocmf/layers/mfdgp_hidden_layer.py:286 and
+ * mobocmf/mlls/variational_elbo_mf.py:40; jitter = CovarianceMatrixMF.add_jitter (layers/...py:17-20).
+ * Zx: M x d; zf: M (kind 1: previous layer's variational mean, layers/...py:556-557) or NULL;
+ * m: M variational mean; Lq: M x M chol_variational_covar (tril applied inside). */
+int mobo_layer_precompute(int kind, int d, int M, const double* Zx, const double* zf, const double* theta,
+                          const double* m, const double* Lq, double jitter, double* ops, void* stream);
+
+/* Backward of mobo_layer_precompute.  gops: gradient buffer (convention above).  work:
+ * mobo_precompute_bwd_work_doubles(M).  Outputs: dtheta[theta size], dzf[M] (kind 1), dm[M], dLq[M x M]. */
+int mobo_layer_precompute_bwd(int kind, int d, int M, const double* Zx, const double* zf, const double* theta,
+                              const double* m, const double* Lq, const double* ops, const double* gops,
+                              double* work, double* dtheta, double* dzf, double* dm, double* dLq, void* stream);
+
+/* Fused row pass of one layer: K(Z_l, X) in shared memory -> mean / variance of q(f) for R rows, with the
+ * reparameterised propagation of the previous layer's sample fused in.
+ * Replaces: MFDGPHiddenLayer.__call__ / forward (mobocmf/layers/mfdgp_hidden_layer.py:232-286) and
+ * UnwhitenedVariationalStrategy.forward's mean/variance [upstream].
+ * x: n x d, row r reads x[r / xrep].  kind 1: f_r = f_direct[r] if f_direct else
+ * mu_prev[r / prep] + sqrt(max(var_prev[r / prep], 1e-10)) * eps[r % eps_mod].
+ * training != 0 selects clamp(k_xx - q, 0).  craw (optional): k_xx - q before the clamp; clamp_count (optional,
+ * device unsigned): incremented per clamped row.  Ksave/Tsave/Usave (optional, all or none): saved for the
+ * backward, mobo_rows_save_doubles(M, R) doubles each. */
+int mobo_layer_rows_fwd(int kind, int d, int M, const double* Zx, const double* zf, const double* theta,
+                        const double* ops, const double* x, int xrep, const double* mu_prev, const double* var_prev,
+                        int prep, const double* eps, long long eps_mod, const double* f_direct, long long R,
+                        int training, double* mu, double* var, double* craw, unsigned int* clamp_count,
+                        double* Ksave, double* Tsave, double* Usave, void* stream);
+
+/* Backward of mobo_layer_rows_fwd given dmu[R], dvar[R].
+ * Outputs: df[R] (kind 1; d loss / d f_r), dxrow[R x d] (optional, d loss / d x per row), dtheta, dzf[M]
+ * (want_param_grads), and the A2 / Ac / dalpha entries of the operator-gradient buffer gops (other entries of
+ * gops are left untouched).  work: mobo_rows_bwd_work_doubles(M, R). */
+int mobo_layer_rows_bwd(int kind, int d, int M, const double* Zx, const double* zf, const double* theta,
+                        const double* ops, const double* x, int xrep, const double* mu_prev, const double* var_prev,
+                        int prep, const double* eps, long long eps_mod, const double* f_direct, long long R,
+                        int training, const double* dmu, const double* dvar, const double* craw,
+                        const unsigned int* clamp_count, const double* Ksave, const double* Tsave,
+                        const double* Usave, int want_param_grads, double* df, double* dxrow, double* dtheta,
+                        double* dzf, double* gops, double* work, void* stream);
+
+/* Dense K(Z_l, Z_l) + jitter I into P (MP x MP) — exposed for tests. */
+int mobo_kzz(int kind, int d, int M, const double* Zx, const double* zf, const double* theta, double jitter,
+             double* P, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,128 @@
+"""JES acquisition over MFDGPs — mirror of ``mobocmf/acquisition_functions/JESMOC_MFDGP.py``
+(``_JES_MFDGP``, ``JESMOC_MFDGP``).  BoTorch is not a dependency: ``_JES_MFDGP`` keeps BoTorch's contract
+(``X (b, 1, d) -> (b,)``, differentiable w.r.t. X) and the multi-start optimiser lives in
+``mobocmf_b200.util.optimize``."""
+import torch
+from torch import Tensor
+
+from ..gp import settings
+from ..models.mfdgp import MFDGP
+
+
+class _JES_MFDGP(torch.nn.Module):
+    def __init__(self, fidelity: int, mfdgp_uncond: MFDGP, mfdgp_cond: MFDGP, model=None) -> None:
+        assert model is None
+        super().__init__()
+        self.fidelity = fidelity
+        self.mfdgp_uncond = mfdgp_uncond
+        self.mfdgp_cond = mfdgp_cond
+
+    def forward(self, X: Tensor) -> Tensor:
+        """0.5 * clamp(log v_uncond - log v_cond, 0)  (acquisition_functions/JESMOC_MFDGP.py:38-52)."""
+        self.mfdgp_uncond.eval()
+        with settings.num_likelihood_samples(1):
+            _, pred_variances_uncond = self.mfdgp_uncond.predict_for_acquisition(X, self.fidelity)
+        self.mfdgp_uncond.train()
+        self.mfdgp_cond.eval()
+        with settings.num_likelihood_samples(1):
+            _, pred_variances_cond = self.mfdgp_cond.predict_for_acquisition(X, self.fidelity)
+        self.mfdgp_cond.train()
+        return 0.5 * torch.clamp(torch.log(pred_variances_uncond) - torch.log(pred_variances_cond), min=0.0)
+
+
+class JESMOC_MFDGP():
+    def __init__(self, model, num_fidelities: int = 1, model_cond=None, standard_bounds=None,
+                 eval_highest_fidelity: bool = False) -> None:
+        self.standard_bounds = standard_bounds
+        self.eval_highest_fidelity = eval_highest_fidelity
+        self.blackbox_mfdgp_fitter_uncond = model.copy_uncond()
+        if model_cond is None:
+            # Pareto-set sampling (RFF + MOOP) is outside the hot path; the fitter must already
+            # hold ``pareto_set`` / ``pareto_front`` (set them, or pass ``model_cond``).
+            if getattr(model, "pareto_set", None) is None:
+                raise RuntimeError("provide model_cond or set model.pareto_set / model.pareto_front first")
+            self.pareto_set, self.pareto_front = model.pareto_set, model.pareto_front
+            model.train_conditioned_mfdgps()
+            self.blackbox_mfdgp_fitter_cond = model
+        else:
+            self.pareto_set = model_cond.pareto_set
+            self.pareto_front = model_cond.pareto_front
+            self.blackbox_mfdgp_fitter_cond = model_cond
+        self.num_fidelities = num_fidelities
+        self.objectives = {}
+        self.constraints = {}
+        self.costs_blackboxes = {}
+        for n_f in range(0, num_fidelities):
+            self.objectives[n_f] = {}
+            self.constraints[n_f] = {}
+            self.costs_blackboxes[n_f] = {}
+            self.costs_blackboxes[n_f]["total"] = 0.0
+
+    def add_blackbox(self, fidelity: int, blackbox_name: str, cost_evaluation: float = 1.0, is_constraint=False):
+        mfdgp_uncond = self.blackbox_mfdgp_fitter_uncond.get_model(blackbox_name, is_constraint=is_constraint)
+        mfdgp_cond = self.blackbox_mfdgp_fitter_cond.get_model(blackbox_name, is_constraint=is_constraint)
+        jes_mfdgp = _JES_MFDGP(fidelity, mfdgp_uncond, mfdgp_cond)
+        if is_constraint:
+            self.constraints[fidelity][blackbox_name] = jes_mfdgp
+        else:
+            self.objectives[fidelity][blackbox_name] = jes_mfdgp
+        self.costs_blackboxes[fidelity]["total"] += cost_evaluation
+        self.costs_blackboxes[fidelity][blackbox_name] = cost_evaluation
+        return jes_mfdgp
+
+    def decoupled_acq(self, X: Tensor, fidelity: int, blackbox_name: str, is_constraint=True) -> Tensor:
+        if is_constraint:
+            return self.constraints[fidelity][blackbox_name](X.double())
+        return self.objectives[fidelity][blackbox_name](X.double())
+
+    def coupled_acq(self, X: Tensor, fidelity: int, float32_accumulator: bool = True) -> Tensor:
+        """Sum over objectives and constraints.  The reference accumulates into a float32 tensor in place
+        (acquisition_functions/JESMOC_MFDGP.py:127-133, quirk Q8); pass ``float32_accumulator=False`` for fp64."""
+        acq = torch.zeros(size=(X.shape[0],), device=X.device,
+                          dtype=torch.float32 if float32_accumulator else torch.float64)
+        for name_obj, obj in self.objectives[fidelity].items():
+            acq = acq + obj(X.double()).to(acq.dtype)
+        for name_con, con in self.constraints[fidelity].items():
+            acq = acq + con(X.double()).to(acq.dtype)
+        return acq
+
+    def _optimize(self, fidelity):
+        from ..util.optimize import optimize_acqf
+        return optimize_acqf(acq_function=lambda x: self.coupled_acq(x, fidelity=fidelity),
+                             bounds=self.standard_bounds, q=1, num_restarts=5, raw_samples=200,
+                             options={"maxiter": 200})
+
+    def _get_nextpoint_coupled_highest_fidelity(self, iteration=None, verbose=False):
+        if verbose:
+            assert (iteration is not None)
+        fidelity_to_evaluate = self.num_fidelities - 1
+        current_candidate, current_value = self._optimize(self.num_fidelities - 1)
+        current_value_weighted = current_value / self.costs_blackboxes[0]["total"]
+        nextpoint = current_candidate[0, :]
+        if verbose:
+            print("Iter:", iteration, "Acquisition: " + str(current_value_weighted.cpu().numpy()) +
+                  " Evaluating fidelity", fidelity_to_evaluate, "at", nextpoint.cpu().numpy())
+        return nextpoint, fidelity_to_evaluate
+
+    def _get_nextpoint_coupled(self, iteration=None, verbose=False):
+        if verbose:
+            assert (iteration is not None)
+        current_value_weighted = 0.0
+        for fidelity in range(self.num_fidelities):
+            new_candidate, new_values = self._optimize(fidelity)
+            new_values_weighted = new_values / self.costs_blackboxes[fidelity]["total"]
+            if (fidelity == 0) or (current_value_weighted < new_values_weighted):
+                fidelity_to_evaluate = fidelity
+                current_value_weighted = new_values_weighted
+                current_candidate = new_candidate
+        nextpoint = current_candidate[0, :]
+        if verbose:
+            print("Iter:", iteration, "Acquisition: " + str(
+                current_value_weighted.cpu().numpy() * self.costs_blackboxes[fidelity_to_evaluate]["total"]) +
+                " Evaluating fidelity", fidelity_to_evaluate, "at", nextpoint.cpu().numpy())
+        return nextpoint, fidelity_to_evaluate
+
+    def get_nextpoint_coupled(self, iteration=None, verbose=False):
+        if self.eval_highest_fidelity:
+            return self._get_nextpoint_coupled_highest_fidelity(iteration=iteration, verbose=verbose)
+        return self._get_nextpoint_coupled(iteration=iteration, verbose=verbose)

@@ -1,0 +1,277 @@
+"""Training orchestration — mirror of ``mobocmf/util/blackbox_mfdgp_fitter.py``: ``MFDGPHandler``,
+``BlackBoxMFDGPFitter`` with the ELBO step (``_update_model``, :156-173), the conditioned step
+(``_update_conditioned_models``, :272-346) and the theta / omega factors (:227-243).  Orchestration stays Python;
+every MFDGP forward / backward inside the steps runs on the sm_100a kernels.
+
+Out of the hot path and therefore not provided here: RFF posterior function sampling + MOOP Pareto-set extraction
+(``sample_and_store_pareto_solution``, :181-225).  Set ``pareto_set`` / ``pareto_front`` on the fitter instead.
+"""
+import sys
+import warnings
+from copy import deepcopy
+
+import numpy as np
+import torch
+
+from ..gp import settings
+from ..mlls.variational_elbo_mf import VariationalELBOMF
+from ..models.mfdgp import MFDGP, TL
+
+ITER_PRINT = 1000
+
+
+def _normal_cdf(x):
+    return 0.5 * (1.0 + torch.erf(x / np.sqrt(2.0)))
+
+
+class _Loader(object):
+    """DataLoader(TensorDataset(x, y, fid), batch_size, shuffle=True) on the device (fitter.py:35-36)."""
+
+    def __init__(self, x, y, f, batch_size, shuffle=True):
+        self.x, self.y, self.f, self.batch_size, self.shuffle = x, y, f, batch_size, shuffle
+
+    def __iter__(self):
+        n = self.x.shape[0]
+        perm = torch.randperm(n, device=self.x.device) if self.shuffle else torch.arange(n, device=self.x.device)
+        for i in range(0, n, self.batch_size):
+            idx = perm[i:i + self.batch_size]
+            yield self.x[idx], self.y[idx], self.f[idx]
+
+
+class MFDGPHandler():
+    MAX_TRIES_FOR_FEASIBLE_GRID = 50
+
+    def __init__(self, x_train, y_train, fidelities_train, num_fidelities, batch_size, type_lengthscale,
+                 previously_trained_model=None, init_params_to_prior_and_fix_them=False,
+                 use_only_highest_fidelity=False, device=None):
+        self.mfdgp = MFDGP(x_train.cpu(), y_train.cpu(), fidelities_train.cpu(), num_fidelities=num_fidelities,
+                           type_lengthscale=type_lengthscale, previously_trained_model=previously_trained_model,
+                           use_only_highest_fidelity=use_only_highest_fidelity,
+                           init_params_to_prior_and_fix_them=init_params_to_prior_and_fix_them)
+        self.mfdgp.double()
+        if device is None:
+            device = x_train.device if x_train.is_cuda else torch.device("cuda")
+        self.device = device
+        self.mfdgp.to(device)
+        self.elbo = VariationalELBOMF(self.mfdgp, x_train.shape[-2], num_fidelities=num_fidelities)
+        self.x, self.y, self.f = x_train.to(device), y_train.to(device), fidelities_train.to(device)
+        self.train_loader = _Loader(self.x, self.y, self.f, batch_size, shuffle=True)
+        self.iter_train_loader = None
+        self.num_data = x_train.shape[0]
+        self.num_fidelities = num_fidelities
+
+
+class BlackBoxMFDGPFitter():
+
+    def __init__(self, num_fidelities, batch_size, lr_1=0.003, lr_2=0.001, num_epochs_1=5000, num_epochs_2=15000,
+                 pareto_set_size=50, opt_grid_size=1000, eps=1e-8, decoupled_evals=False,
+                 type_lengthscale=TL.MEDIAN, device=None):
+        self.num_obj = 0
+        self.num_con = 0
+        self.models_uncond_trained = False
+        self.mfdgp_handlers_objs = {}
+        self.mfdgp_handlers_cons = {}
+        self.device = device
+        self.thresholds_cons = torch.tensor([], dtype=torch.double)
+        self.x_train = None
+        self.objs_train = torch.tensor([], dtype=torch.double)
+        self.cons_train = torch.tensor([], dtype=torch.double)
+        self.num_fidelities = num_fidelities
+        self.batch_size = batch_size
+        self.points_to_sample = batch_size
+        self.lr_1, self.lr_2 = lr_1, lr_2
+        self.num_epochs_1, self.num_epochs_2 = num_epochs_1, num_epochs_2
+        self.pareto_set_size = pareto_set_size
+        self.opt_grid_size = opt_grid_size
+        self.eps = eps
+        self.decoupled_evals = decoupled_evals
+        self.type_lengthscale = type_lengthscale
+        self.pareto_set = None
+        self.pareto_front = None
+        self.verbose = True
+
+    def initialize_mfdgp(self, x_train, y_train, fidelities, blackbox_name, threshold_constraint=0.0,
+                         is_constraint=False, previously_trained_model=None,
+                         init_params_to_prior_and_fix_them=False, use_only_highest_fidelity=False):
+        if self.x_train is None:
+            self.x_train = x_train
+        else:
+            assert torch.equal(self.x_train, x_train), "The inputs for this new mfdgp do not match with inputs " \
+                "for previous mfdgp models. This class is not currently prepared for a decoupled evaluation setting."
+        handler = MFDGPHandler(x_train, y_train, fidelities, self.num_fidelities, self.batch_size,
+                               type_lengthscale=self.type_lengthscale,
+                               previously_trained_model=previously_trained_model,
+                               init_params_to_prior_and_fix_them=init_params_to_prior_and_fix_them,
+                               use_only_highest_fidelity=use_only_highest_fidelity, device=self.device)
+        if is_constraint:
+            self.cons_train = torch.cat((self.cons_train, y_train.cpu()), 1)
+            self.mfdgp_handlers_cons[blackbox_name] = handler
+            self.thresholds_cons = torch.cat((self.thresholds_cons,
+                                              torch.tensor([threshold_constraint], dtype=torch.double)), 0)
+            self.num_con += 1
+        else:
+            self.objs_train = torch.cat((self.objs_train, y_train.cpu()), 1)
+            self.mfdgp_handlers_objs[blackbox_name] = handler
+            self.num_obj += 1
+
+    # ---- the ELBO step (fitter.py:156-173) ----
+    @staticmethod
+    def _update_model(model, elbo, optimizer, train_loader, eps=None):
+        loss_iter = 0.0
+        kl_iter = 0.0
+        for (x_batch, y_batch, fidelities) in train_loader:
+            with settings.num_likelihood_samples(1):
+                optimizer.zero_grad()
+                output = model(x_batch, eps=eps)
+                res = elbo(output, y_batch.T, fidelities)
+                loss, kl = -res[0], res[1]
+                loss.backward()
+                optimizer.step()
+                loss_iter += loss.detach()
+                kl_iter += kl.detach()
+        return loss_iter, kl_iter
+
+    def _train_mfdgp(self, func_update_model, fix_variational_hypers, num_epochs, lr):
+        for kind, handlers in (("OBJ", self.mfdgp_handlers_objs), ("CON", self.mfdgp_handlers_cons)):
+            opts = []
+            for h in handlers.values():
+                h.mfdgp.fix_variational_hypers(fix_variational_hypers)
+                opts.append(torch.optim.Adam([{'params': h.mfdgp.parameters()}], lr=lr))
+            for n, (h, optimizer) in enumerate(zip(handlers.values(), opts)):
+                for i in range(num_epochs):
+                    loss_iter, kl_iter = func_update_model(h.mfdgp, h.elbo, optimizer, h.train_loader)
+                    if self.verbose and ((i % ITER_PRINT) == 0 or ((i + 1) == num_epochs)):
+                        print("[%s: " % kind, n, "] Epoch:", i, "/", num_epochs, ". Avg. Neg. ELBO per epoch:",
+                              loss_iter.item(), "\t KL per epoch:", kl_iter.item())
+                        sys.stdout.flush()
+
+    def train_mfdgps(self):
+        self._train_mfdgp(self._update_model, fix_variational_hypers=True, num_epochs=self.num_epochs_1,
+                          lr=self.lr_1)
+        self._train_mfdgp(self._update_model, fix_variational_hypers=False, num_epochs=self.num_epochs_2,
+                          lr=self.lr_2)
+        self.models_uncond_trained = True
+
+    def sample_and_store_pareto_solution(self):
+        raise NotImplementedError("Pareto-set sampling (RFF + MOOP) is outside the B200 hot path (SURVEY.md §8); "
+                                  "set fitter.pareto_set / fitter.pareto_front")
+
+    # ---- theta / omega factors (fitter.py:227-243) ----
+    def loss_theta_factors(self, cs_mean, cs_var, threshold):
+        gamma_c_star = (cs_mean - threshold) / torch.sqrt(cs_var)
+        cdf = _normal_cdf(gamma_c_star)
+        return torch.sum(np.log(1.0 - self.eps) * cdf + np.log(self.eps) * (1.0 - cdf))
+
+    def loss_omega_factors(self, fs_mean, fs_var, cs_mean, cs_var, pareto_front):
+        thr = self.thresholds_cons.to(cs_mean.device)
+        gamma_c = (cs_mean - thr[:, None]) / torch.sqrt(cs_var)
+        gamma_f_star = (pareto_front[:, :, None] - fs_mean) / torch.sqrt(fs_var)
+        prod = torch.prod(_normal_cdf(gamma_c), 0) * torch.prod(_normal_cdf(gamma_f_star), 1)
+        return torch.sum(np.log(self.eps) * prod + np.log(1 - self.eps) * (1.0 - prod))
+
+    # ---- the conditioned step (fitter.py:272-346) ----
+    def conditioned_loss(self, handlers_objs, handlers_cons, x_tilde=None, batches=None, eps=None):
+        """Loss of one conditioned iteration.  ``batches`` / ``eps`` (optional, for parity tests): per black box the
+        minibatch ``(x, y, fid)`` and a dict ``{"batch", "pareto", "tilde"}`` of per-layer normals."""
+        handlers_objs, handlers_cons = list(handlers_objs), list(handlers_cons)
+        dev = handlers_objs[0].device if handlers_objs else handlers_cons[0].device
+        pareto_set = self.pareto_set.to(dev)
+        pareto_front = self.pareto_front.to(dev)
+        thr = self.thresholds_cons.to(dev)
+        if x_tilde is None:
+            x_tilde = torch.rand(size=(10, pareto_set.shape[1]), device=dev).double()
+        loss = 0.0
+
+        def next_batch(h, key):
+            if batches is not None:
+                return batches[key]
+            try:
+                return next(h.iter_train_loader)
+            except Exception:
+                h.iter_train_loader = iter(h.train_loader)
+                return next(h.iter_train_loader)
+
+        def e(key, which):
+            return None if eps is None else eps[key][which]
+
+        for i, h in enumerate(handlers_objs):
+            key = ("obj", i)
+            x_batch, y_batch, fidelities = next_batch(h, key)
+            with settings.num_likelihood_samples(1):
+                output = h.mfdgp(x_batch, eps=e(key, "batch"))
+                loss = loss + -h.elbo(output, y_batch.T, fidelities)[0] / x_batch.shape[0] * h.num_data
+                output = h.mfdgp(pareto_set, eps=e(key, "pareto"))
+                pareto_fidelities = torch.ones(size=(pareto_front.shape[0], 1), device=dev) * (h.num_fidelities - 1)
+                loss = loss + -h.elbo(output, pareto_front[:, i:(i + 1)].T, pareto_fidelities,
+                                      include_kl_term=False)
+        for k, h in enumerate(handlers_cons):
+            key = ("con", k)
+            x_batch, y_batch, fidelities = next_batch(h, key)
+            with settings.num_likelihood_samples(1):
+                output = h.mfdgp(x_batch, eps=e(key, "batch"))
+                loss = loss + -h.elbo(output, y_batch.T, fidelities)[0] / x_batch.shape[0] * h.num_data
+                output = h.mfdgp(pareto_set, eps=e(key, "pareto"))[h.num_fidelities - 1]
+                loss = loss + -self.loss_theta_factors(output.mean, output.variance, thr[k])
+        fm, fv, cm, cv = [], [], [], []
+        for i, h in enumerate(handlers_objs):
+            with settings.num_likelihood_samples(1):
+                output = h.mfdgp(x_tilde, eps=e(("obj", i), "tilde"))[h.num_fidelities - 1]
+            fm.append(output.mean[None, :]); fv.append(output.variance[None, :])
+        for k, h in enumerate(handlers_cons):
+            with settings.num_likelihood_samples(1):
+                output = h.mfdgp(x_tilde, eps=e(("con", k), "tilde"))[h.num_fidelities - 1]
+            cm.append(output.mean[None, :]); cv.append(output.variance[None, :])
+        z = torch.zeros(0, x_tilde.shape[0], dtype=torch.double, device=dev)
+        loss = loss + -self.loss_omega_factors(torch.cat(fm, 0) if fm else z, torch.cat(fv, 0) if fv else z,
+                                               torch.cat(cm, 0) if cm else z, torch.cat(cv, 0) if cv else z,
+                                               pareto_front)
+        return loss
+
+    def _update_conditioned_models(self, handlers_objs, handlers_cons, optimizer):
+        optimizer.zero_grad()
+        loss = self.conditioned_loss(handlers_objs, handlers_cons)
+        loss.backward()
+        optimizer.step()
+        return loss.detach()
+
+    def _train_conditioned_mfdgps(self, func_update_model, fix_variational_hypers, num_iters, lr):
+        params = list()
+        for h in list(self.mfdgp_handlers_objs.values()) + list(self.mfdgp_handlers_cons.values()):
+            h.mfdgp.fix_variational_hypers_cond(fix_variational_hypers)
+            params = params + list(h.mfdgp.parameters())
+        optimizer = torch.optim.Adam([{'params': params}], lr=lr)
+        for i in range(num_iters):
+            loss_iter = func_update_model(self.mfdgp_handlers_objs.values(), self.mfdgp_handlers_cons.values(),
+                                          optimizer)
+            if self.verbose and ((i % ITER_PRINT) == 0 or ((i + 1) == num_iters)):
+                print("Iter:", i, "/", num_iters, ". Neg. ELBO per iter:", loss_iter.item())
+                sys.stdout.flush()
+
+    def train_conditioned_mfdgps(self):
+        self._train_conditioned_mfdgps(self._update_conditioned_models, fix_variational_hypers=True,
+                                       num_iters=self.num_epochs_2, lr=self.lr_2)
+        for h in list(self.mfdgp_handlers_objs.values()) + list(self.mfdgp_handlers_cons.values()):
+            h.iter_train_loader = None
+
+    def mfdgps_to_train_mode(self):
+        for h in list(self.mfdgp_handlers_objs.values()) + list(self.mfdgp_handlers_cons.values()):
+            h.mfdgp.train()
+
+    def copy_uncond(self):
+        if self.models_uncond_trained is False:
+            warnings.warn("(Warning) The mfdgp models have not been trained yet.")
+        handlers = list(self.mfdgp_handlers_objs.values()) + list(self.mfdgp_handlers_cons.values())
+        for h in handlers:
+            h.mfdgp.eval()
+            h.iter_train_loader = None
+        self_copy = deepcopy(self)
+        for h in handlers:
+            h.mfdgp.train()
+        for h in list(self_copy.mfdgp_handlers_objs.values()) + list(self_copy.mfdgp_handlers_cons.values()):
+            h.mfdgp.train()
+        return self_copy
+
+    def get_model(self, name: str, is_constraint=False):
+        if is_constraint:
+            return self.mfdgp_handlers_cons[name].mfdgp
+        return self.mfdgp_handlers_objs[name].mfdgp

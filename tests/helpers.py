@@ -1,0 +1,126 @@
+"""Shared builders for the parity tests: random but well-defined MFDGP states in GPyTorch's state_dict naming."""
+import numpy as np
+import torch
+
+from oracle import mfdgp_oracle as O
+
+
+def random_state(M, d, L, seed=0, ls=0.5, lq_scale=0.05, dtype=torch.float64):
+    """A random L-layer MFDGP state with shared inducing inputs (so quirk Q4 holds: Z_l = [Z, m_{l-1}])."""
+    g = torch.Generator().manual_seed(seed)
+    Zx = torch.rand(M, d, generator=g, dtype=dtype)
+    sd = {}
+    for l in range(L):
+        p = "hidden_layer_%d." % l
+        c = p + "covar_module."
+
+        def rawpos(lo, hi, shape):
+            v = lo + (hi - lo) * torch.rand(shape, generator=g, dtype=dtype)
+            return O.inv_softplus(v)
+
+        if l == 0:
+            sd[c + "raw_outputscale"] = rawpos(0.8, 1.5, ())
+            sd[c + "base_kernel.raw_lengthscale"] = rawpos(0.7 * ls, 1.3 * ls, (1, d))
+            Z = Zx.clone()
+        else:
+            sd[c + "kernels.0.kernels.0.raw_outputscale"] = rawpos(0.7, 1.3, ())
+            sd[c + "kernels.0.kernels.0.base_kernel.raw_lengthscale"] = rawpos(1.5 * ls, 3.0 * ls, (1, d))
+            sd[c + "kernels.0.kernels.1.kernels.0.raw_variance"] = rawpos(0.5, 1.2, (1, 1))
+            sd[c + "kernels.0.kernels.1.kernels.1.raw_outputscale"] = rawpos(0.6, 1.2, ())
+            sd[c + "kernels.0.kernels.1.kernels.1.base_kernel.raw_lengthscale"] = rawpos(0.7, 1.3, (1, 1))
+            sd[c + "kernels.1.raw_outputscale"] = rawpos(0.05, 0.2, ())
+            sd[c + "kernels.1.base_kernel.raw_lengthscale"] = rawpos(0.7 * ls, 1.3 * ls, (1, d))
+            Z = torch.cat([Zx, torch.zeros(M, 1, dtype=dtype)], 1)    # stored last column is ignored at run time
+        sd[p + "variational_strategy.inducing_points"] = Z
+        q = p + "variational_strategy._variational_distribution."
+        sd[q + "variational_mean"] = torch.randn(M, generator=g, dtype=dtype)
+        Lq = torch.tril(torch.randn(M, M, generator=g, dtype=dtype)) * lq_scale / np.sqrt(M)
+        Lq = Lq + torch.diag(0.05 + 0.1 * torch.rand(M, generator=g, dtype=dtype))
+        # strictly-upper garbage must be ignored (CholeskyVariationalDistribution masks with tril)
+        sd[q + "chol_variational_covar"] = Lq + torch.triu(torch.randn(M, M, generator=g, dtype=dtype), 1)
+        sd["hidden_layer_likelihood_%d.noise_covar.raw_noise" % l] = torch.randn(1, generator=g, dtype=dtype)
+    noise_upper = [0.1 + 0.02 * l for l in range(L)]
+    return sd, noise_upper
+
+
+def param_keys(sd):
+    return [k for k, v in sd.items() if v.dtype.is_floating_point and "inducing_points" not in k]
+
+
+def clone_state(sd, device=None, requires_grad=False):
+    out = {}
+    for k, v in sd.items():
+        t = v.detach().clone()
+        if device is not None:
+            t = t.to(device)
+        if requires_grad and t.dtype.is_floating_point and "inducing_points" not in k:
+            t.requires_grad_(True)
+        out[k] = t
+    return out
+
+
+def relerr(a, b):
+    a = a.detach().cpu().double()
+    b = b.detach().cpu().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fixtures from the reference's examples
+# ------------------------------------------------------------------------------------------------------------
+def forrester_data():
+    """Deterministic data of examples/example_acquisition_mfdgp_forrester/...py:51-104 (config C2)."""
+    def mf1(x):
+        return ((6 * x - 2) ** 2) * np.sin(12 * x - 4)
+
+    def mf0(x):
+        return 0.5 * mf1(x) + 10 * (x - 0.5) + 5
+    x0 = np.linspace(0, 1.0, 12).reshape(12, 1)
+    x1 = np.array([0.1, 0.3, 0.5, 0.7]).reshape(4, 1)
+    out = {}
+    for name, f0, f1 in (("obj1", mf0, mf1), ("obj2", lambda x: -mf0(x), lambda x: -mf1(x)),
+                         ("con1", lambda x: np.sin(x * np.pi * 2.5), lambda x: np.cos(x * np.pi * 2.5))):
+        y0, y1 = f0(x0), f1(x1)
+        mean, std = np.mean(np.vstack((y1, y0))), np.std(np.vstack((y1, y0)))
+        out[name] = torch.cat((torch.from_numpy((y1 - mean) / std), torch.from_numpy((y0 - mean) / std)), 0).double()
+    x = torch.cat((torch.from_numpy(x1), torch.from_numpy(x0)), 0).double()
+    fid = torch.cat((torch.ones(4).double(), torch.zeros(12).double()))[:, None]
+    return x, out, fid
+
+
+def synthetic_data(n_per_fid, d, seed=0):
+    """Seeded closed-form multi-fidelity data (SURVEY.md §8d C4 recipe), ordering: all fidelities concatenated."""
+    g = torch.Generator().manual_seed(seed)
+    L = len(n_per_fid)
+    xs, ys, fs = [], [], []
+    for l, n in enumerate(n_per_fid):
+        x = torch.rand(n, d, generator=g, dtype=torch.float64)
+        y0 = torch.sin(2 * np.pi * x).sum(1) / np.sqrt(d)
+        y1 = 0.8 * y0 + 0.2 * torch.cos(np.pi * x.sum(1))
+        y2 = y1 ** 2 - 0.5 * y1 + 0.1 * x[:, 0]
+        y = [y0, y1, y2][min(l, 2)] + 1e-2 * torch.randn(n, generator=g, dtype=torch.float64)
+        xs.append(x); ys.append(y[:, None]); fs.append(torch.full((n, 1), float(l), dtype=torch.float64))
+    del L
+    return torch.cat(xs), torch.cat(ys), torch.cat(fs)
+
+
+def oracle_view(model):
+    """CPU copy of a product model's parameters for the oracle: (sd, noise_lower, noise_upper, samples)."""
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items() if "previous_layer" not in k}
+    L = model.num_fidelities
+    lo = [float(sd["hidden_layer_likelihood_%d.noise_covar.raw_noise_constraint.lower_bound" % l]) for l in range(L)]
+    up = [float(sd["hidden_layer_likelihood_%d.noise_covar.raw_noise_constraint.upper_bound" % l]) for l in range(L)]
+    samples = [getattr(model, "hidden_layer_%d" % l).samples.detach().cpu() for l in range(L)]
+    return sd, lo, up, samples
+
+
+def parity_tol(model, base=1e-10):
+    """fp64 parity bar: 1e-10 relative on well-conditioned inputs, cond(K_zz + jitter I) * eps-scaled otherwise
+    (SURVEY.md §7 'Hard parts': two algebraically identical fp64 formulations already differ by ~cond * eps)."""
+    sd, _, _, _ = oracle_view(model)
+    worst = 1.0
+    for l in range(model.num_fidelities):
+        Z = O.layer_inducing_points(sd, l)
+        P = O.layer_kernel(sd, l, Z, Z) + O.JITTER * torch.eye(Z.shape[0], dtype=torch.float64)
+        worst = max(worst, float(torch.linalg.cond(P)))
+    return max(base, 20 * 2.2e-16 * worst), worst

@@ -1,0 +1,69 @@
+"""GPU parity of the conditioned training step (util/blackbox_mfdgp_fitter.py:272-346) against the oracle."""
+import pytest
+import torch
+
+from oracle import mfdgp_oracle as O
+from tests.helpers import forrester_data, oracle_view, relerr, parity_tol
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_conditioned_step_loss_and_grads():
+    from mobocmf_b200.util.blackbox_mfdgp_fitter import BlackBoxMFDGPFitter
+    x, ys, fid = forrester_data()
+    N, L = x.shape[0], 2
+    torch.manual_seed(0)
+    fitter = BlackBoxMFDGPFitter(L, N, num_epochs_1=0, num_epochs_2=0, device=torch.device(DEV))
+    fitter.verbose = False
+    fitter.initialize_mfdgp(x, ys["obj1"], fid, "obj1")
+    fitter.initialize_mfdgp(x, ys["obj2"], fid, "obj2")
+    fitter.initialize_mfdgp(x, ys["con1"], fid, "con1", threshold_constraint=0.1, is_constraint=True)
+    g = torch.Generator().manual_seed(3)
+    P, T = 7, 10
+    fitter.pareto_set = torch.rand(P, 1, generator=g, dtype=torch.float64)
+    fitter.pareto_front = torch.randn(P, 2, generator=g, dtype=torch.float64)
+    x_tilde = torch.rand(T, 1, generator=g, dtype=torch.float64)
+    hobjs = list(fitter.mfdgp_handlers_objs.values())
+    hcons = list(fitter.mfdgp_handlers_cons.values())
+    for h in hobjs + hcons:
+        h.mfdgp.fix_variational_hypers_cond(True)
+        with torch.no_grad():
+            for n, p in h.mfdgp.named_parameters():
+                if "variational_mean" in n:
+                    p.add_(0.1 * torch.randn(p.shape, generator=g, dtype=p.dtype).to(DEV))
+    batches, eps, eps_o = {}, {}, {}
+    for key, h in [(("obj", i), h) for i, h in enumerate(hobjs)] + [(("con", k), h) for k, h in enumerate(hcons)]:
+        perm = torch.randperm(N, generator=g)
+        batches[key] = (h.x[perm.to(DEV)], h.y[perm.to(DEV)], h.f[perm.to(DEV)])
+        e = {"batch": [None, torch.randn(1, N, generator=g)], "pareto": [None, torch.randn(1, P, generator=g)],
+             "tilde": [None, torch.randn(1, T, generator=g)]}
+        eps_o[key] = e
+        eps[key] = {k: [None, v[1].to(DEV)] for k, v in e.items()}
+    loss = fitter.conditioned_loss(hobjs, hcons, x_tilde=x_tilde.to(DEV), batches=batches, eps=eps)
+    loss.backward()
+
+    def omod(key, h):
+        sd, lo, up, _ = oracle_view(h.mfdgp)
+        for n, p in h.mfdgp.named_parameters():
+            if p.requires_grad:
+                sd[n].requires_grad_(True)
+        xb, yb, fb = [t.cpu() for t in batches[key]]
+        return dict(sd=sd, num_layers=L, noise_upper=up, num_data=N, batch=(xb, yb, fb),
+                    eps_batch=eps_o[key]["batch"], eps_pareto=eps_o[key]["pareto"], eps_tilde=eps_o[key]["tilde"])
+    objs = [omod(("obj", i), h) for i, h in enumerate(hobjs)]
+    cons = [omod(("con", k), h) for k, h in enumerate(hcons)]
+    loss_o = O.conditioned_step_loss(objs, cons, fitter.pareto_set, fitter.pareto_front, fitter.thresholds_cons,
+                                     x_tilde, eps_factor=fitter.eps)
+    loss_o.backward()
+    tol = max(parity_tol(h.mfdgp)[0] for h in hobjs + hcons)
+    assert relerr(loss, loss_o) < tol, (relerr(loss, loss_o), tol)
+    for mod, h in zip(objs + cons, hobjs + hcons):
+        for n, p in h.mfdgp.named_parameters():
+            if not p.requires_grad:
+                assert p.grad is None
+                continue
+            gp, go = p.grad, mod["sd"][n].grad
+            if "chol_variational_covar" in n:
+                gp, go = torch.tril(gp), torch.tril(go)
+            assert relerr(gp, go) < 1e3 * tol, (n, relerr(gp, go), tol)
