@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the MFDGP hot path on B200:  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[3], SURVEY.md §8d "C4"): scaled MFDGP training, d=6, 3 fidelities, N=50 000
+synthetic points, M=256 inducing inputs, minibatch B=1024 rows x S=64 MC samples, fp64.  One STEP = the body of
+``_update_model`` (mobocmf/util/blackbox_mfdgp_fitter.py:161-171): zero-grad, forward, ELBO, backward, Adam.
+With N GPUs every rank processes its own 1024-row minibatch (weak scaling) and the parameter gradients are summed
+with one NCCL all-reduce, i.e. one global step over N*1024 rows; ``value`` counts 1024-row step units per second.
+
+The second headline of BASELINE.json (JESMOC acquisition evals/s, configs[4] "C5") is measured on a slice and
+reported under ``"acq"`` in the same JSON line.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C4 = dict(N=50000, d=6, L=3, M=256, B=1024, S=64, fid_sizes=(30000, 15000, 5000), lengthscale=0.3, seed=0)
+FP64_PEAK_TFLOPS = 37.1   # measured DMMA.8x8x4 pipe peak on this pool's B200 (profiles/r01_fp64_probe.log);
+#                           cuBLAS DGEMM reaches 35.4 (profiles/r01_dgemm_probe.log).  MEASURED_PEAKS.json has no fp64 entry.
+
+
+def c4_data(cfg):
+    """SURVEY.md §8d C4 recipe: seeded closed-form 3-fidelity targets on U[0,1]^6, rows shuffled so that the first M
+    rows (the inducing inputs) are a random subset."""
+    g = torch.Generator().manual_seed(cfg["seed"])
+    N, d = cfg["N"], cfg["d"]
+    x = torch.rand(N, d, generator=g, dtype=torch.float64)
+    fid = torch.cat([torch.full((n,), float(l)) for l, n in enumerate(cfg["fid_sizes"])]).double()
+    y0 = torch.sin(2 * math.pi * x).sum(1) / math.sqrt(d)
+    y1 = 0.8 * y0 + 0.2 * torch.cos(math.pi * x.sum(1))
+    y2 = y1 ** 2 - 0.5 * y1 + 0.1 * x[:, 0]
+    y = torch.where(fid == 0, y0, torch.where(fid == 1, y1, y2)) + 1e-2 * torch.randn(N, generator=g).double()
+    perm = torch.randperm(N, generator=g)
+    return x[perm].contiguous(), y[perm][:, None].contiguous(), fid[perm][:, None].contiguous()
+
+
+def build_model(cfg, x, y, fid, device):
+    from mobocmf_b200.models.mfdgp import MFDGP
+    torch.manual_seed(cfg["seed"])
+    model = MFDGP(x, y, fid, cfg["L"], num_inducing=cfg["M"], init_lengthscale=cfg["lengthscale"])
+    model.double()
+    return model.to(device)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def step_flops(cfg):
+    """Algorithmic flops of one step: per (row, layer) forward F = 2 M^2 + 2 M + 3 d_l M, rows
+    R_tot = B + (L-1) B S, step ~ 3 F R_tot + 12 L M^3."""
+    M, B, S, L, d = cfg["M"], cfg["B"], cfg["S"], cfg["L"], cfg["d"]
+    f0 = 2 * M * M + 2 * M + 3 * d * M
+    f1 = 2 * M * M + 2 * M + 3 * (d + 1) * M
+    return 3 * (f0 * B + (L - 1) * f1 * B * S) + 12 * L * M ** 3, f1
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from mobocmf_b200 import _lib
+    from mobocmf_b200.gp import settings
+    from mobocmf_b200.mlls.variational_elbo_mf import VariationalELBOMF
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = dict(C4)
+    x, y, fid = c4_data(cfg)
+    model = build_model(cfg, x, y, fid, dev)
+    elbo = VariationalELBOMF(model, cfg["N"], cfg["L"])
+    model.fix_variational_hypers(False)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam([{"params": params}], lr=0.001)
+    xd, yd, fd = x.to(dev), y.to(dev), fid.to(dev)
+    B, S, N = cfg["B"], cfg["S"], cfg["N"]
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # pinned host staging for the end-to-end arm
+    xh, yh, fh = x.pin_memory(), y.pin_memory(), fid.pin_memory()
+
+    def one_step(xb, yb, fb):
+        opt.zero_grad(set_to_none=True)
+        with settings.num_likelihood_samples(1):
+            out = model(xb, num_samples=S)
+            res = elbo(out, yb.T, fb)
+        loss = -res[0]
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            off = 0
+            for p in params:
+                n = p.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                off += n
+        opt.step()
+        return loss
+
+    def device_step():
+        idx = torch.randint(0, N, (B,), device=dev, generator=g)
+        return one_step(xd[idx], yd[idx], fd[idx])
+
+    hb = [torch.empty(B, cfg["d"], dtype=torch.float64).pin_memory(), torch.empty(B, 1, dtype=torch.float64).pin_memory(),
+          torch.empty(B, 1, dtype=torch.float64).pin_memory()]
+    gh = torch.Generator().manual_seed(99 + rank)
+
+    def e2e_step():
+        idx = torch.randint(0, N, (B,), generator=gh)
+        torch.index_select(xh, 0, idx, out=hb[0]); torch.index_select(yh, 0, idx, out=hb[1])
+        torch.index_select(fh, 0, idx, out=hb[2])
+        xb, yb, fb = (t.to(dev, non_blocking=True) for t in hb)
+        return float(one_step(xb, yb, fb))       # device -> host read of the step's loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(device_step, args.steps)
+    launches = _lib.launch_count() - l0
+    if sampler:
+        sampler.stop_flag = True
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # per-kernel CUDA-event timing of a few extra steps (launch stream = torch's current stream)
+    prof = {}
+    if rank == 0:
+        _lib.profile_enable(True)
+        nprof = min(args.steps, 5)
+        for _ in range(nprof):
+            device_step()
+        torch.cuda.synchronize()
+        for name, t in _lib.profile_collect():
+            prof.setdefault(name, []).append(t)
+        _lib.profile_enable(False)
+
+    # acquisition slice (C5-shaped): n candidates x S=25 samples through an (uncond, cond) pair at the top fidelity
+    acq = None
+    if rank == 0 and not args.no_acq:
+        acq = bench_acq(model, dev, cfg)
+
+    if rank == 0:
+        flops, f1 = step_flops(cfg)
+        ms_step = ms / args.steps
+        out = {
+            "metric": "mfdgp_elbo_steps_per_s", "value": world * args.steps / (ms / 1e3), "unit": "steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 scaled MFDGP training: d=6, 3 fidelities, N=50000, M=256, B=1024 rows x S=64 "
+                                   "MC samples per GPU (step unit = 1024 x 64), lengthscale 0.3, Adam lr 1e-3",
+                       "global_batch": world * B, "parallelism": "dp%d rows sharded, grads all-reduced" % world,
+                       "cache": "per-step working set (3 x 134 MB saved tiles per upper layer) exceeds L2"},
+            "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": "steps/s",
+                    "h2d_bytes_per_step": B * (cfg["d"] + 2) * 8, "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary() if sampler else None,
+            "step_tflops": flops / (ms_step * 1e-3) / 1e12,
+        }
+        if prof:
+            tot = {k: sum(v) for k, v in prof.items()}
+            top = max((k for k in tot if k.startswith("row_")), key=lambda k: tot[k])
+            per_launch_ms = tot[top] / len(prof[top])
+            rows = B * S
+            alg = (1 if "fwd" in top else 2) * f1 * rows        # forward F per row; backward = 2 F per row
+            out["roofline"] = {"bound": "tensor", "kernel": top, "achieved": alg / (per_launch_ms * 1e-3) / 1e12,
+                               "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                               "frac": alg / (per_launch_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS, "traffic": None,
+                               "peak_source": "measured DMMA fp64 pipe peak, profiles/r01_fp64_probe.log "
+                                              "(MEASURED_PEAKS.json has no fp64 figure)",
+                               "launch_ms": per_launch_ms}
+            nst = min(args.steps, 5)
+            out["kernel_ms_per_step"] = {k: round(v / nst, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}
+        if acq:
+            out["acq"] = acq
+        if not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(cfg, x, y, fid, model)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_acq(model, dev, cfg, n=20000, iters=3):
+    """JESMOC acquisition evals/s on a C5-shaped slice: n candidates x 25 samples, one (uncond, cond) MFDGP pair at
+    fidelity 2; one 'eval' = one candidate through _JES_MFDGP.forward (2 models x (1 + 25 + 25) rows)."""
+    import copy
+    from mobocmf_b200.acquisition_functions.JESMOC_MFDGP import _JES_MFDGP
+    cond = copy.deepcopy(model)
+    with torch.no_grad():
+        for nme, p in cond.named_parameters():
+            if "chol_variational_covar" in nme:
+                p.mul_(0.7)
+    acq = _JES_MFDGP(cfg["L"] - 1, model, cond)
+    X = torch.rand(n, 1, cfg["d"], device=dev, dtype=torch.float64)
+    with torch.no_grad():
+        acq(X)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            acq(X)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"metric": "jesmoc_acq_evals_per_s", "value": n / (ms * 1e-3), "unit": "evals/s (1 black box, 1 Pareto "
+            "sample, forward)", "candidates": n, "ms": ms}
+
+
+def cpu_baseline(cfg, x, y, fid, model, max_seconds=30.0):
+    """The oracle's tiled S-sample ELBO step (forward + autograd backward + Adam) on the host cores, on a bounded
+    sample of the same workload: same model / B / M, S reduced to S_cpu and scaled by rows."""
+    from oracle import mfdgp_oracle as O
+    from tests.helpers import oracle_view
+    sd, lo, up, _ = oracle_view(model)
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    for n in names:
+        sd[n].requires_grad_(True)
+    B, S_cpu, N, L = cfg["B"], 8, cfg["N"], cfg["L"]
+    g = torch.Generator().manual_seed(5)
+    opt = torch.optim.Adam([sd[n] for n in names], lr=0.001)
+    times = []
+    t_start = time.time()
+    for it in range(4):
+        idx = torch.randint(0, N, (B,), generator=g)
+        eps = [None] + [torch.randn(B * S_cpu, generator=g).double() for _ in range(1, L)]
+        t0 = time.time()
+        opt.zero_grad()
+        loss, _ = O.elbo_step_loss_tiled(sd, L, up, x[idx], y[idx], fid[idx], eps, N, S_cpu, noise_lower=lo)
+        loss.backward()
+        opt.step()
+        times.append(time.time() - t0)
+        if time.time() - t_start > max_seconds:
+            break
+    t = min(times[1:]) if len(times) > 1 else times[0]
+    rows_full = B + (L - 1) * B * cfg["S"]
+    rows_cpu = B + (L - 1) * B * S_cpu
+    t_full = t * rows_full / rows_cpu
+    return {"value": 1.0 / t_full, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "oracle tiled ELBO step (fwd+autograd bwd+Adam), B=1024, M=256, S=%d instead of 64 "
+                      "(%.2f s/step), scaled by rows x%.2f" % (S_cpu, t, rows_full / rows_cpu)}
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path.  GPyTorch/BoTorch are not installable here
+    (SURVEY.md §8c), so this times the oracle port with all host threads on the same config, each step a bounded
+    sample (S=8 of 64 samples, scaled by rows)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = dict(C4)
+    x, y, fid = c4_data(cfg)
+    from mobocmf_b200.models.mfdgp import MFDGP
+    torch.manual_seed(cfg["seed"])
+    model = MFDGP(x, y, fid, cfg["L"], num_inducing=cfg["M"], init_lengthscale=cfg["lengthscale"])
+    model.double()
+    cb = cpu_baseline(cfg, x, y, fid, model, max_seconds=120.0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    out = {"impl": "reference", "metric": "mfdgp_elbo_steps_per_s", "value": cb["value"], "unit": "steps/s",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "C4 scaled MFDGP training: d=6, 3 fidelities, N=50000, M=256, B=1024 rows x S=64 "
+                                  "MC samples (CPU oracle port; GPyTorch not installable)"},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-acq", action="store_true", help="skip the acquisition slice")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,13 @@ extern "C" {
 /* library / build identification: returns 100 for sm_100a */
 int mobo_abi_version(void);
 
+/* Launch accounting: number of kernels this library has launched in this process; optional per-launch CUDA-event
+ * timing (enable, run, then collect: NUL-separated kernel names into `names`, milliseconds into `ms`; returns the
+ * number of records written and clears the log).  Used by bench.py for `gpu_launches` and the roofline kernel. */
+long long mobo_launch_count(void);
+void mobo_profile_enable(int on);
+int mobo_profile_collect(char* names, size_t names_bytes, float* ms, int max_records);
+
 int mobo_padded_m(int M);
 size_t mobo_ops_doubles(int M);
 /* doubles needed for each of Ksave / Tsave / Usave of mobo_layer_rows_fwd for R rows */

@@ -19,6 +19,9 @@ _c_sz = ctypes.c_size_t
 
 _SIGNATURES = {
     "mobo_abi_version": (_c_i, []),
+    "mobo_launch_count": (_c_ll, []),
+    "mobo_profile_enable": (None, [_c_i]),
+    "mobo_profile_collect": (_c_i, [ctypes.c_char_p, _c_sz, ctypes.POINTER(ctypes.c_float), _c_i]),
     "mobo_padded_m": (_c_i, [_c_i]),
     "mobo_ops_doubles": (_c_sz, [_c_i]),
     "mobo_rows_save_doubles": (_c_sz, [_c_i, _c_ll]),
@@ -77,3 +80,20 @@ def check(code, what):
         raise RuntimeError("mobocmf_b200: %s failed with code %d (%s)" %
                            (what, code, {-1: "CUDA launch error", -2: "unsupported shape: M <= 256, d <= 8"}.get(
                                code, "unknown")))
+
+
+def launch_count():
+    return int(load().mobo_launch_count())
+
+
+def profile_enable(on):
+    load().mobo_profile_enable(1 if on else 0)
+
+
+def profile_collect(max_records=200000):
+    """[(kernel name, milliseconds)] of every launch since profiling was enabled (synchronises)."""
+    names = ctypes.create_string_buffer(64 * max_records)
+    ms = (ctypes.c_float * max_records)()
+    n = load().mobo_profile_collect(names, len(names), ms, max_records)
+    raw = names.raw.split(b"\0")
+    return [(raw[i].decode(), float(ms[i])) for i in range(n)]

@@ -1,5 +1,6 @@
 // extern "C" entry points of libmobocmf_b200.so (declared in include/mobocmf_b200.h) and the host-side kernel
 // sequences behind them.
+#include <string.h>
 #include "../../include/mobocmf_b200.h"
 #include "matrix_ops.cu"
 #include "row_pass.cu"
@@ -12,6 +13,33 @@ static inline int padded(int M) { return ((M + 31) / 32) * 32; }
 extern "C" {
 
 int mobo_abi_version(void) { return 100; }
+
+long long mobo_launch_count(void) { return prof_state().launches; }
+
+void mobo_profile_enable(int on) { prof_state().on = on != 0; }
+
+int mobo_profile_collect(char* names, size_t names_bytes, float* ms, int max_records) {
+  ProfState& s = prof_state();
+  int n = 0;
+  size_t off = 0;
+  for (ProfRec& r : s.recs) {
+    cudaEventSynchronize(r.e1);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    if (n < max_records) {
+      const size_t len = strlen(r.name) + 1;
+      if (off + len <= names_bytes) {
+        memcpy(names + off, r.name, len);
+        off += len;
+        ms[n++] = t;
+      }
+    }
+    s.pool.push_back(r.e0);
+    s.pool.push_back(r.e1);
+  }
+  s.recs.clear();
+  return n;
+}
 int mobo_padded_m(int M) { return padded(M); }
 size_t mobo_ops_doubles(int M) { return ops_size(padded(M)); }
 
@@ -34,7 +62,7 @@ int mobo_kzz(int kind, int d, int M, const double* Zx, const double* zf, const d
              double* P, void* stream) {
   const int MP = padded(M);
   if (d > kMaxD || MP > MAX_MP) return -2;
-  kzz_kernel<<<(MP * MP + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kind, d, M, MP, Zx, zf, theta, jitter, P);
+  MOBO_LAUNCH("kzz_kernel", (cudaStream_t)stream, kzz_kernel<<<(MP * MP + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kind, d, M, MP, Zx, zf, theta, jitter, P));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -58,14 +86,14 @@ int mobo_layer_precompute(int kind, int d, int M, const double* Zx, const double
   }
   MOBO_TRY(mobo_kzz(kind, d, M, Zx, zf, theta, jitter, P, stream));
   const size_t chol_smem = (size_t)(CH_NB * (CH_NB + 1) + 8 + (size_t)(MP - CH_NB) * CH_LDP) * sizeof(double);
-  chol_kernel<<<1, CH_THREADS, chol_smem, st>>>(P, L, MP, ops + ops_scal(MP));
+  MOBO_LAUNCH("chol_kernel", st, chol_kernel<<<1, CH_THREADS, chol_smem, st>>>(P, L, MP, ops + ops_scal(MP)));
   const size_t tri_smem = (size_t)(MP / 32) * 32 * 36 * sizeof(double);
-  trtri_kernel<<<1, TI_THREADS, tri_smem, st>>>(L, W, MP);
+  MOBO_LAUNCH("trtri_kernel", st, trtri_kernel<<<1, TI_THREADS, tri_smem, st>>>(L, W, MP));
   MOBO_TRY(ew(EW_TRANSPOSE, M, MP, W, nullptr, WT, nullptr, 1.0, nullptr, nullptr, st));
   MOBO_TRY(ew(EW_PAD_TRIL, M, MP, Lq, nullptr, LQ, nullptr, 1.0, nullptr, nullptr, st));
   MOBO_TRY(gemm(MP, W, false, LQ, false, H, 1.0, 0.0, st));
   MOBO_TRY(ew(EW_TRANSPOSE, M, MP, H, nullptr, HT, nullptr, 1.0, nullptr, nullptr, st));
-  finalize_kernel<<<1, 256, 0, st>>>(M, MP, m, ops);
+  MOBO_LAUNCH("finalize_kernel", st, finalize_kernel<<<1, 256, 0, st>>>(M, MP, m, ops));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -106,7 +134,7 @@ int mobo_layer_precompute_bwd(int kind, int d, int M, const double* Zx, const do
   MOBO_TRY(ew(EW_SCALE, M, MP, H, nullptr, T4, dkl, 1.0, nullptr, nullptr, st));
   MOBO_TRY(gemm(MP, W, false, T3, true, T4, 1.0, 1.0, st));
   // dbeta = W dalpha + dkl beta ; dm = W^T dbeta
-  dbeta_kernel<<<1, 256, 0, st>>>(M, MP, ops, dalpha, dkl, dbeta, dm);
+  MOBO_LAUNCH("dbeta_kernel", st, dbeta_kernel<<<1, 256, 0, st>>>(M, MP, ops, dalpha, dkl, dbeta, dm));
   cudaMemsetAsync(mpad, 0, sizeof(double) * MP, st);
   cudaMemcpyAsync(mpad, m, sizeof(double) * M, cudaMemcpyDeviceToDevice, st);
   // dW = -2 W A1 + H dY + beta dalpha^T + dbeta m^T + dH Lq^T   (lower triangle kept)
@@ -118,7 +146,7 @@ int mobo_layer_precompute_bwd(int kind, int d, int M, const double* Zx, const do
   MOBO_TRY(ew(EW_TRIL_INPLACE, M, MP, T5, nullptr, T5, nullptr, 1.0, nullptr, nullptr, st));
   // dLq = tril(W^T dH) - dkl diag(1 / Lq_ii)
   MOBO_TRY(gemm(MP, WT, false, T4, false, T6, 1.0, 0.0, st));
-  dlq_extract_kernel<<<(M * M + 255) / 256, 256, 0, st>>>(M, MP, T6, LQ, dkl, dLq);
+  MOBO_LAUNCH("dlq_extract_kernel", st, dlq_extract_kernel<<<(M * M + 255) / 256, 256, 0, st>>>(M, MP, T6, LQ, dkl, dLq));
   // dL = -tril(W^T dW W^T) + dkl diag(1 / L_ii)
   MOBO_TRY(gemm(MP, WT, false, T5, false, T1, 1.0, 0.0, st));
   MOBO_TRY(gemm(MP, T1, false, WT, false, T2, 1.0, 0.0, st));
@@ -131,7 +159,7 @@ int mobo_layer_precompute_bwd(int kind, int d, int M, const double* Zx, const do
   MOBO_TRY(ew(EW_SYM, M, MP, T2, nullptr, T3, nullptr, 1.0, nullptr, nullptr, st));
   // through K(Z, Z)
   const int nblk = (M + KZB_WARPS - 1) / KZB_WARPS;
-  kzz_bwd_kernel<<<nblk, KZB_WARPS * 32, 0, st>>>(kind, d, M, MP, Zx, zf, theta, T3, part, dzf, 0);
+  MOBO_LAUNCH("kzz_bwd_kernel", st, kzz_bwd_kernel<<<nblk, KZB_WARPS * 32, 0, st>>>(kind, d, M, MP, Zx, zf, theta, T3, part, dzf, 0));
   MOBO_TRY(launch_reduce_partials(part, nblk, theta_size(kind, d), 5 + 2 * kMaxD, dtheta, 0, st));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -7,7 +7,35 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace mobo {
+
+// ---- launch accounting / optional per-launch CUDA-event timing (mobo_profile_* in the C ABI) ----
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+struct ProfState {
+  bool on = false;
+  long long launches = 0;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+};
+inline ProfState& prof_state() { static ProfState s; return s; }
+inline cudaEvent_t prof_event() {
+  ProfState& s = prof_state();
+  if (!s.pool.empty()) { cudaEvent_t e = s.pool.back(); s.pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+inline void prof_begin(const char* name, cudaStream_t st) {
+  ProfState& s = prof_state();
+  ++s.launches;
+  if (s.on) { ProfRec r{name, prof_event(), prof_event()}; cudaEventRecord(r.e0, st); s.recs.push_back(r); }
+}
+inline void prof_end(cudaStream_t st) {
+  ProfState& s = prof_state();
+  if (s.on) cudaEventRecord(s.recs.back().e1, st);
+}
+// every kernel launch of the library goes through this macro
+#define MOBO_LAUNCH(name, st, ...) do { mobo::prof_begin(name, st); __VA_ARGS__; mobo::prof_end(st); } while (0)
 
 constexpr int kMaxD = 8;               // max number of x columns (ARD dims) handled by the kernels
 constexpr double kMinVariance = 1e-10; // gpytorch settings.min_variance (fp64), quirk Q9

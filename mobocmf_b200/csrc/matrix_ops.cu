@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(GM_THREADS) gemm_kernel(int n, const double* _
 static int gemm(int n, const double* A, bool tA, const double* B, bool tB, double* C, double alpha, double beta,
                 cudaStream_t st) {
   dim3 grid((n + GM_T - 1) / GM_T, (n + GM_T - 1) / GM_T);
-  gemm_kernel<<<grid, GM_THREADS, 0, st>>>(n, A, tA ? 1 : n, tA ? n : 1, B, tB ? 1 : n, tB ? n : 1, C, alpha, beta);
+  MOBO_LAUNCH("gemm_kernel", st, gemm_kernel<<<grid, GM_THREADS, 0, st>>>(n, A, tA ? 1 : n, tA ? n : 1, B, tB ? 1 : n, tB ? n : 1, C, alpha, beta));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -466,7 +466,7 @@ __global__ void ew_kernel(int op, int M, int MP, const double* __restrict__ in, 
 
 static int ew(int op, int M, int MP, const double* in, const double* in2, double* out, const double* sdev, double hs,
               const double* v1, const double* v2, cudaStream_t st) {
-  ew_kernel<<<(MP * MP + 255) / 256, 256, 0, st>>>(op, M, MP, in, in2, out, sdev, hs, v1, v2);
+  MOBO_LAUNCH("ew_kernel", st, ew_kernel<<<(MP * MP + 255) / 256, 256, 0, st>>>(op, M, MP, in, in2, out, sdev, hs, v1, v2));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -699,7 +699,7 @@ int launch_row_fwd(const RowArgs& a, cudaStream_t st) {
     attr_done = true;
   }
   if (a.R <= 0) return 0;
-  row_fwd_kernel<<<row_grid(a.R), ROW_THREADS, smem, st>>>(a);
+  MOBO_LAUNCH("row_fwd_kernel", st, row_fwd_kernel<<<row_grid(a.R), ROW_THREADS, smem, st>>>(a));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -715,15 +715,19 @@ int launch_row_bwd(const RowArgs& a, int grid, cudaStream_t st) {
     attr_done = true;
   }
   if (a.R <= 0) return 0;
-  if (a.want_param_grads && a.want_x_grads) row_bwd_kernel<true, true><<<grid, ROW_THREADS, smem, st>>>(a);
-  else if (a.want_x_grads) row_bwd_kernel<false, true><<<grid, ROW_THREADS, smem, st>>>(a);
-  else row_bwd_kernel<true, false><<<grid, ROW_THREADS, smem, st>>>(a);
+  if (a.want_param_grads && a.want_x_grads) {
+    MOBO_LAUNCH("row_bwd_kernel<param,x>", st, row_bwd_kernel<true, true><<<grid, ROW_THREADS, smem, st>>>(a));
+  } else if (a.want_x_grads) {
+    MOBO_LAUNCH("row_bwd_kernel<x>", st, row_bwd_kernel<false, true><<<grid, ROW_THREADS, smem, st>>>(a));
+  } else {
+    MOBO_LAUNCH("row_bwd_kernel<param>", st, row_bwd_kernel<true, false><<<grid, ROW_THREADS, smem, st>>>(a));
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 int launch_reduce_partials(const double* part, int nblocks, int n, int stride, double* out, int accumulate,
                            cudaStream_t st) {
-  reduce_partials_kernel<<<(n + 127) / 128, 128, 0, st>>>(part, nblocks, n, stride, out, accumulate);
+  MOBO_LAUNCH("reduce_partials_kernel", st, reduce_partials_kernel<<<(n + 127) / 128, 128, 0, st>>>(part, nblocks, n, stride, out, accumulate));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -749,11 +753,11 @@ int launch_syrk(const double* K, const double* dvar, const double* craw, int whi
                 double* dalpha, cudaStream_t st) {
   const int nt = syrk_ntiles(MP), nc = syrk_nchunk(MP, R);
   dim3 grid(nt, nc);
-  syrk_kernel<<<grid, SY_THREADS, 0, st>>>(K, dvar, craw, which, MP, R, nc, part, clamp_count, dmu,
-                                           which == 0 ? part_alpha : nullptr);
-  syrk_reduce_kernel<<<(MP * MP + 255) / 256, 256, 0, st>>>(part, nt, nc, MP, A, which, clamp_count);
+  MOBO_LAUNCH("syrk_kernel", st, syrk_kernel<<<grid, SY_THREADS, 0, st>>>(K, dvar, craw, which, MP, R, nc, part, clamp_count, dmu,
+                                           which == 0 ? part_alpha : nullptr));
+  MOBO_LAUNCH("syrk_reduce_kernel", st, syrk_reduce_kernel<<<(MP * MP + 255) / 256, 256, 0, st>>>(part, nt, nc, MP, A, which, clamp_count));
   if (which == 0 && part_alpha && dalpha)
-    reduce_partials_kernel<<<(MP + 127) / 128, 128, 0, st>>>(part_alpha, nc, MP, MP, dalpha, 0);
+    MOBO_LAUNCH("reduce_partials_kernel", st, reduce_partials_kernel<<<(MP + 127) / 128, 128, 0, st>>>(part_alpha, nc, MP, MP, dalpha, 0));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

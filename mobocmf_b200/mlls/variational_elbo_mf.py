@@ -18,7 +18,14 @@ class VariationalELBOMF(object):
             mask = fidelities.T == i
             if mask.sum() != 0:
                 likelihood = getattr(self.model, self.model.name_hidden_layer_likelihood + str(i))
-                data_term = data_term + likelihood.expected_log_prob(target, l_approximate_dist_f[i])[mask].sum()
+                dist = l_approximate_dist_f[i]
+                S = getattr(dist, "samples_per_point", 1)
+                if S > 1:   # S-sample extension: average the per-sample terms of each point
+                    ell = likelihood.expected_log_prob(target.reshape(-1, 1).expand(-1, S).reshape(-1), dist)
+                    ell = ell.reshape(-1, S).mean(1)[None, :]
+                else:
+                    ell = likelihood.expected_log_prob(target, dist)
+                data_term = data_term + ell[mask].sum()
         if include_kl_term is False:
             return data_term
         kl_divergence = self.model.variational_strategy.kl_divergence()

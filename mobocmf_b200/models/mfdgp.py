@@ -39,8 +39,14 @@ class MFDGP(nn.Module):
 
     def __init__(self, x_train, y_train, fidelities, num_fidelities, type_lengthscale=TL.MEDIAN,
                  num_samples_for_acquisition=25, previously_trained_model=None, ini_inducing_using_layer_0=False,
-                 use_only_highest_fidelity=False, init_params_to_prior_and_fix_them=False):
+                 use_only_highest_fidelity=False, init_params_to_prior_and_fix_them=False, num_inducing=None,
+                 init_lengthscale=None):
+        """Reference signature (models/mfdgp.py:22-25) plus two extensions the reference lacks:
+        ``num_inducing`` keeps only the first M training inputs as inducing inputs (the reference always uses all
+        N, models/mfdgp.py:297-298) and ``init_lengthscale`` overrides the O(N^2) median heuristic."""
         super().__init__()
+        self.num_inducing = num_inducing
+        self._init_lengthscale_override = init_lengthscale
         hidden_layers = []
         self.init_params_to_prior_and_fix_them = init_params_to_prior_and_fix_them
         self._eval_mode = False
@@ -98,6 +104,8 @@ class MFDGP(nn.Module):
         return _DeepGPVariationalStrategy(self)
 
     def get_init_lengthscale(self, type_lengthscale, inputs=None):
+        if self._init_lengthscale_override is not None:
+            return torch.as_tensor(self._init_lengthscale_override, dtype=torch.float64)
         if type_lengthscale == TL.ONES:
             return torch.ones(self.input_dims)
         elif type_lengthscale == TL.MEDIAN:
@@ -118,10 +126,14 @@ class MFDGP(nn.Module):
             getattr(self, self.name_hidden_layer + str(i)).eval_mode()
         self._eval_mode = True
 
-    def forward(self, inputs, max_fidelity=None, eps=None):
+    def forward(self, inputs, max_fidelity=None, eps=None, num_samples=1):
         """models/mfdgp.py:174-196.  ``eps`` (optional): list indexed by layer of the training-mode normals
-        (reference: float32 ``torch.normal`` of shape (1, B), quirk Q6)."""
+        (reference: float32 ``torch.normal`` of shape (1, B), quirk Q6).  ``num_samples`` = S > 1 (not in the
+        reference, which always trains with one sample): layer 0 runs on the B rows, the upper
+        layers on B*S rows (row b*S+s = point b, sample s) with independent normals per (row, layer)."""
         num_layers = self.num_hidden_layers if max_fidelity is None else max_fidelity + 1
+        if num_samples > 1:
+            return self._forward_multisample(inputs, num_layers, eps, num_samples)
         l_outputs = [None] * num_layers
         output_layer = None
         for i in range(num_layers):
@@ -134,6 +146,28 @@ class MFDGP(nn.Module):
                 output_layer = hidden_layer(inputs, output_layer, eps=None if eps is None else eps[i])
             l_outputs[i] = output_layer
         return l_outputs
+
+    def _forward_multisample(self, inputs, num_layers, eps, S):
+        B = inputs.shape[0]
+        x = inputs.contiguous()
+        outs = []
+        layer0 = getattr(self, self.name_hidden_layer + "0")
+        mu, var = layer0._moments(x)
+        ns = settings.num_likelihood_samples.value_()
+        outs.append(GaussianMoments(mu.unsqueeze(0).expand(ns, -1), var.unsqueeze(0).expand(ns, -1)))
+        R = B
+        for i in range(1, num_layers):
+            layer = getattr(self, self.name_hidden_layer + str(i))
+            e = None if eps is None else eps[i]
+            if e is None:
+                e = torch.randn(B * S, device=x.device, dtype=torch.float32)
+            e = e.to(device=x.device, dtype=torch.float64).reshape(-1).contiguous()
+            mu, var = layer._moments(x, mu, var, e, xrep=S, prep=(B * S) // R, eps_mod=B * S, R=B * S)
+            R = B * S
+            d = GaussianMoments(mu, var)
+            d.samples_per_point = S
+            outs.append(d)
+        return outs
 
     def fix_variational_hypers(self, value):
         for i in range(self.num_hidden_layers):
@@ -197,6 +231,8 @@ class MFDGP(nn.Module):
         ``|a|^2 - 2 a.b + |b|^2`` (first minimum wins, like argmin); float32 values (quirk Q1)."""
         sel = fidelities[:, 0] == layer
         inducing_points = x_train[sel, :] if self.use_only_highest_fidelity is True else x_train
+        if self.num_inducing is not None:
+            inducing_points = inducing_points[:self.num_inducing]
         xs, ys = x_train[sel, :], y_train[sel, :]
         d = (xs ** 2).sum(1, keepdim=True) - 2.0 * xs.mm(inducing_points.T) + (inducing_points ** 2).sum(1)[None, :]
         to_sel = torch.argmin(d, dim=0)

@@ -345,6 +345,36 @@ def elbo_step_loss_multisample(sd, num_layers, noise_upper, x_batch, y_batch, fi
     return sum(losses) / len(losses), kls[0]
 
 
+def elbo_step_loss_tiled(sd, num_layers, noise_upper, x_batch, y_batch, fid_batch, eps, num_data, S,
+                         noise_lower=NOISE_LOWER, jitter=JITTER):
+    """The same S-sample ELBO evaluated the way a CPU user would: layer 0 once on the B rows, upper layers on the
+    B*S tiled rows (row b*S+s), data terms averaged over s.  eps[l]: (B*S,) normals of layer l.  Used as the CPU
+    baseline of config C4 and cross-checked against :func:`elbo_step_loss_multisample`."""
+    B = x_batch.shape[0]
+    mean, var = layer_q(sd, 0, x_batch, True, jitter)
+    outs = [(mean, var)]
+    x_tile = x_batch.repeat_interleave(S, 0)
+    pm, pv = mean.repeat_interleave(S, 0), var.repeat_interleave(S, 0)
+    for l in range(1, num_layers):
+        f = (eps[l].to(x_batch.dtype).reshape(-1) * torch.sqrt(read_variance(pv)) + pm).reshape(-1, 1)
+        pm, pv = layer_q(sd, l, torch.cat([x_tile, f], -1), True, jitter)
+        outs.append((pm, pv))
+    data_term = 0.0
+    y = y_batch.reshape(-1)
+    for l in range(num_layers):
+        mask = fid_batch.reshape(-1) == l
+        if mask.sum() != 0:
+            noise = likelihood_noise(sd, l, noise_upper, noise_lower)
+            m_, v_ = outs[l]
+            if l == 0:
+                ell = expected_log_prob(y, m_, read_variance(v_), noise)
+            else:
+                ell = expected_log_prob(y.repeat_interleave(S, 0), m_, read_variance(v_), noise).reshape(B, S).mean(1)
+            data_term = data_term + ell[mask].sum()
+    kl = kl_divergence(sd, num_layers, jitter)
+    return -(data_term - kl * B / num_data), kl * B / num_data
+
+
 def adam_step(params, grads, state, lr, betas=(0.9, 0.999), eps=1e-8):
     """torch.optim.Adam defaults (fitter.py:126,132,259), restated for the fused-Adam parity test."""
     state["step"] = state.get("step", 0) + 1
