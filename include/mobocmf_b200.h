@@ -13,11 +13,12 @@
  *           theta = [a1, v_lin, a_f, l_f, a2, l1_0 .. l1_{d-1}, l2_0 .. l2_{d-1}]
  *   theta holds CONSTRAINED values (softplus already applied); d = number of x columns (without f).
  *   MP = M rounded up to a multiple of 32.  An "operator buffer" is mobo_ops_doubles(M) doubles laid out as
- *   [L | W | WT | H | HT | P | LQ] (seven MP x MP row-major blocks), beta[MP], alpha[MP], scal[16]
+ *   [L | W | WT | H | HT | P | LQ] (seven MP x MP row-major blocks), beta[MP], alpha[MP], scal[16], rowstat[4 MP]
  *   (scal[0] = KL, scal[5] = Cholesky status: 0 ok, 1 not positive definite).
  *   The GRADIENT of an operator buffer uses the same layout and, by convention, carries only
- *   block W: A2 = sum_r dvar_r k_r k_r^T, block H: the same sum over clamped rows, alpha: sum_r dmu_r k_r,
- *   scal[0]: d loss / d KL.
+ *   block W: A2 = sum_r dvar_r t_r t_r^T (t = W k, whitened), block H: the same sum over clamped rows,
+ *   alpha: b = sum_r dmu_r t_r,
+ *   scal[0]: d loss / d KL, scal[6]: number of clamped rows behind block H.
  */
 #ifndef MOBOCMF_B200_H
 #define MOBOCMF_B200_H
@@ -38,7 +39,7 @@ int mobo_profile_collect(char* names, size_t names_bytes, float* ms, int max_rec
 
 int mobo_padded_m(int M);
 size_t mobo_ops_doubles(int M);
-/* doubles needed for each of Ksave / Tsave / Usave of mobo_layer_rows_fwd for R rows */
+/* doubles needed for each of Tsave / Usave of mobo_layer_rows_fwd for R rows */
 size_t mobo_rows_save_doubles(int M, long long R);
 /* scratch doubles for mobo_layer_rows_bwd / mobo_layer_precompute_bwd */
 size_t mobo_rows_bwd_work_doubles(int M, long long R);
@@ -53,6 +54,17 @@ size_t mobo_precompute_bwd_work_doubles(int M);
 int mobo_layer_precompute(int kind, int d, int M, const double* Zx, const double* zf, const double* theta,
                           const double* m, const double* Lq, double jitter, double* ops, void* stream);
 
+/* The same for all layers of a model in one batch of launches (the layers' operator chains are independent).
+ * Arrays of length nl (HOST arrays of device pointers); zf[i] is NULL for kind 0. */
+int mobo_model_precompute(int nl, const int* kinds, int d, int M, const double* const* Zx, const double* const* zf,
+                          const double* const* theta, const double* const* m, const double* const* Lq,
+                          double jitter, double* const* ops, void* stream);
+int mobo_model_precompute_bwd(int nl, const int* kinds, int d, int M, const double* const* Zx,
+                              const double* const* zf, const double* const* theta, const double* const* m,
+                              const double* const* Lq, const double* const* ops, const double* const* gops,
+                              double* const* work, double* const* dtheta, double* const* dzf, double* const* dm,
+                              double* const* dLq, void* stream);
+
 /* Backward of mobo_layer_precompute.  gops: gradient buffer (convention above).  work:
  * mobo_precompute_bwd_work_doubles(M).  Outputs: dtheta[theta size], dzf[M] (kind 1), dm[M], dLq[M x M]. */
 int mobo_layer_precompute_bwd(int kind, int d, int M, const double* Zx, const double* zf, const double* theta,
@@ -66,13 +78,13 @@ int mobo_layer_precompute_bwd(int kind, int d, int M, const double* Zx, const do
  * x: n x d, row r reads x[r / xrep].  kind 1: f_r = f_direct[r] if f_direct else
  * mu_prev[r / prep] + sqrt(max(var_prev[r / prep], 1e-10)) * eps[r % eps_mod].
  * training != 0 selects clamp(k_xx - q, 0).  craw (optional): k_xx - q before the clamp; clamp_count (optional,
- * device unsigned): incremented per clamped row.  Ksave/Tsave/Usave (optional, all or none): saved for the
+ * device unsigned): incremented per clamped row.  Tsave/Usave (optional, both or none): t = W k and u = H^T t saved for the
  * backward, mobo_rows_save_doubles(M, R) doubles each. */
 int mobo_layer_rows_fwd(int kind, int d, int M, const double* Zx, const double* zf, const double* theta,
                         const double* ops, const double* x, int xrep, const double* mu_prev, const double* var_prev,
                         int prep, const double* eps, long long eps_mod, const double* f_direct, long long R,
                         int training, double* mu, double* var, double* craw, unsigned int* clamp_count,
-                        double* Ksave, double* Tsave, double* Usave, void* stream);
+                        double* Tsave, double* Usave, void* stream);
 
 /* Backward of mobo_layer_rows_fwd given dmu[R], dvar[R].
  * Outputs: df[R] (kind 1; d loss / d f_r), dxrow[R x d] (optional, d loss / d x per row), dtheta, dzf[M]
@@ -82,7 +94,7 @@ int mobo_layer_rows_bwd(int kind, int d, int M, const double* Zx, const double* 
                         const double* ops, const double* x, int xrep, const double* mu_prev, const double* var_prev,
                         int prep, const double* eps, long long eps_mod, const double* f_direct, long long R,
                         int training, const double* dmu, const double* dvar, const double* craw,
-                        const unsigned int* clamp_count, const double* Ksave, const double* Tsave,
+                        const unsigned int* clamp_count, const double* Tsave,
                         const double* Usave, int want_param_grads, double* df, double* dxrow, double* dtheta,
                         double* dzf, double* gops, double* work, void* stream);
 

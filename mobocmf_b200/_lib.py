@@ -30,12 +30,14 @@ _SIGNATURES = {
     "mobo_kzz": (_c_i, [_c_i, _c_i, _c_i, _c_dp, _c_dp, _c_dp, _c_d, _c_dp, _c_dp]),
     "mobo_layer_precompute": (_c_i, [_c_i, _c_i, _c_i, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_d, _c_dp, _c_dp]),
     "mobo_layer_precompute_bwd": (_c_i, [_c_i, _c_i, _c_i] + [_c_dp] * 13),
+    "mobo_model_precompute": (_c_i, [_c_i, _c_dp, _c_i, _c_i, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_d, _c_dp, _c_dp]),
+    "mobo_model_precompute_bwd": (_c_i, [_c_i, _c_dp, _c_i, _c_i] + [_c_dp] * 13),
     "mobo_layer_rows_fwd": (_c_i, [_c_i, _c_i, _c_i, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_i, _c_dp, _c_dp, _c_i,
                                    _c_dp, _c_ll, _c_dp, _c_ll, _c_i, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
-                                   _c_dp, _c_dp]),
+                                   _c_dp]),
     "mobo_layer_rows_bwd": (_c_i, [_c_i, _c_i, _c_i, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_i, _c_dp, _c_dp, _c_i,
                                    _c_dp, _c_ll, _c_dp, _c_ll, _c_i, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
-                                   _c_dp, _c_i, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
+                                   _c_i, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -97,3 +99,16 @@ def profile_collect(max_records=200000):
     n = load().mobo_profile_collect(names, len(names), ms, max_records)
     raw = names.raw.split(b"\0")
     return [(raw[i].decode(), float(ms[i])) for i in range(n)]
+
+
+def ptr_array(tensors):
+    """HOST array of device pointers (None -> NULL) for the batched entry points."""
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        p = ptr(t)
+        arr[i] = None if p is None else p.value
+    return arr
+
+
+def int_array(values):
+    return (ctypes.c_int * len(values))(*values)

@@ -55,113 +55,192 @@ size_t mobo_rows_bwd_work_doubles(int M, long long R) {
 
 size_t mobo_precompute_bwd_work_doubles(int M) {
   const int MP = padded(M);
-  return (size_t)6 * MP * MP + 2 * MP + (size_t)((M + KZB_WARPS - 1) / KZB_WARPS) * (5 + 2 * kMaxD) + 64;
+  return (size_t)8 * MP * MP + (size_t)((M + KZB_WARPS - 1) / KZB_WARPS) * KZB_NTH + 64;
+}
+
+static int fill_batch(LayerBatch& b, int nl, const int* kinds, int d, int M, const double* const* Zx,
+                      const double* const* zf, const double* const* theta, const double* const* m,
+                      const double* const* Lq, double* const* ops) {
+  if (nl < 1 || nl > MAX_BATCH) return -2;
+  b.n = nl; b.d = d; b.M = M; b.MP = padded(M);
+  if (d > kMaxD || b.MP > MAX_MP) return -2;
+  for (int i = 0; i < MAX_BATCH; ++i) {
+    const bool ok = i < nl;
+    b.kind[i] = ok ? kinds[i] : 0;
+    b.Zx[i] = ok ? Zx[i] : nullptr;
+    b.zf[i] = (ok && zf) ? zf[i] : nullptr;
+    b.theta[i] = ok ? theta[i] : nullptr;
+    b.m[i] = (ok && m) ? m[i] : nullptr;
+    b.Lq[i] = (ok && Lq) ? Lq[i] : nullptr;
+    b.ops[i] = (ok && ops) ? ops[i] : nullptr;
+  }
+  return 0;
 }
 
 int mobo_kzz(int kind, int d, int M, const double* Zx, const double* zf, const double* theta, double jitter,
              double* P, void* stream) {
+  // P is written where block OPS_P of an operator buffer starting at (P - OPS_P * MP^2) would live
+  LayerBatch b;
   const int MP = padded(M);
-  if (d > kMaxD || MP > MAX_MP) return -2;
-  MOBO_LAUNCH("kzz_kernel", (cudaStream_t)stream, kzz_kernel<<<(MP * MP + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kind, d, M, MP, Zx, zf, theta, jitter, P));
+  double* fake_ops = P - ops_block(MP, OPS_P);
+  MOBO_TRY(fill_batch(b, 1, &kind, d, M, &Zx, &zf, &theta, nullptr, nullptr, &fake_ops));
+  cudaStream_t st = (cudaStream_t)stream;
+  MOBO_LAUNCH("kzz_kernel", st, kzz_kernel<<<dim3((MP * MP + 255) / 256, 1), 256, 0, st>>>(b, jitter, OPS_P));
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int mobo_model_precompute(int nl, const int* kinds, int d, int M, const double* const* Zx, const double* const* zf,
+                          const double* const* theta, const double* const* m, const double* const* Lq,
+                          double jitter, double* const* ops, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  LayerBatch b;
+  MOBO_TRY(fill_batch(b, nl, kinds, d, M, Zx, zf, theta, m, Lq, ops));
+  const int MP = b.MP;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_done = true;
+  }
+  const dim3 ew_grid((MP * MP + 255) / 256, nl);
+  MOBO_LAUNCH("kzz_kernel", st, kzz_kernel<<<ew_grid, 256, 0, st>>>(b, jitter, OPS_P));
+  const size_t chol_smem = (size_t)(64 * CH_LD + (size_t)MP * CH_LD) * sizeof(double);
+  MOBO_LAUNCH("chol_inv_kernel", st, chol_inv_kernel<<<nl, CH_THREADS, chol_smem, st>>>(b));
+  MOBO_LAUNCH("padtril_kernel", st, padtril_kernel<<<ew_grid, 256, 0, st>>>(b));
+  GemmOperand A, B;
+  double* C[MAX_BATCH]; double* Ct[MAX_BATCH];
+  FinBatch f;
+  for (int i = 0; i < MAX_BATCH; ++i) {
+    const bool ok = i < nl;
+    A.p[i] = ok ? ops[i] + ops_block(MP, OPS_W) : nullptr;
+    B.p[i] = ok ? ops[i] + ops_block(MP, OPS_LQ) : nullptr;
+    C[i] = ok ? ops[i] + ops_block(MP, OPS_H) : nullptr;
+    Ct[i] = ok ? ops[i] + ops_block(MP, OPS_HT) : nullptr;
+    f.rowstat[i] = ok ? ops[i] + ops_rowstat(MP) : nullptr;
+    f.counter[i] = ok ? reinterpret_cast<unsigned int*>(ops[i] + ops_scal(MP) + SC_COUNTER) : nullptr;
+  }
+  A.trans = false; A.tri = 1; B.trans = false; B.tri = 1;
+  MOBO_TRY(gemm_batched(nl, MP, A, B, C, Ct, 1.0, 0.0, nullptr, st));
+  MOBO_LAUNCH("finalize_kernel", st,
+              finalize_kernel<<<dim3((MP + FIN_WARPS - 1) / FIN_WARPS, nl), FIN_WARPS * 32, 0, st>>>(b, f));
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int mobo_model_precompute_bwd(int nl, const int* kinds, int d, int M, const double* const* Zx,
+                              const double* const* zf, const double* const* theta, const double* const* m,
+                              const double* const* Lq, const double* const* ops, const double* const* gops,
+                              double* const* work, double* const* dtheta, double* const* dzf, double* const* dm,
+                              double* const* dLq, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  LayerBatch b;
+  MOBO_TRY(fill_batch(b, nl, kinds, d, M, Zx, zf, theta, m, Lq, const_cast<double* const*>(ops)));
+  const int MP = b.MP;
+  const size_t MP2 = (size_t)MP * MP;
+  enum { T_G2 = 0, T_V, T_NN, T_F, T_X1, T_DP, T_X2, T_Y2, T_N };
+  auto blk = [&](int i, int which) { return work[i] + (size_t)which * MP2; };
+  auto mk = [&](GemmOperand& o, bool trans, int tri, auto getter) {
+    o.trans = trans; o.tri = tri;
+    for (int i = 0; i < MAX_BATCH; ++i) o.p[i] = i < nl ? getter(i) : nullptr;
+  };
+  double* C[MAX_BATCH];
+  auto outs = [&](int which) { for (int i = 0; i < MAX_BATCH; ++i) C[i] = i < nl ? blk(i, which) : nullptr; };
+  GemmOperand A, B;
+  // G2 = H H^T
+  mk(A, false, 1, [&](int i) { return ops[i] + ops_block(MP, OPS_H); });
+  mk(B, true, 2, [&](int i) { return ops[i] + ops_block(MP, OPS_H); });
+  outs(T_G2);
+  MOBO_TRY(gemm_batched(nl, MP, A, B, C, nullptr, 1.0, 0.0, nullptr, st));
+  // V = A2 G2
+  mk(A, false, 0, [&](int i) { return gops[i] + ops_block(MP, OPS_W); });
+  mk(B, false, 0, [&](int i) { return (const double*)blk(i, T_G2); });
+  outs(T_V);
+  MOBO_TRY(gemm_batched(nl, MP, A, B, C, nullptr, 1.0, 0.0, nullptr, st));
+  // whitened core N and F = 2 A2 + g I
+  {
+    CombineBatch c;
+    for (int i = 0; i < MAX_BATCH; ++i) {
+      const bool ok = i < nl;
+      c.A2[i] = ok ? gops[i] + ops_block(MP, OPS_W) : nullptr;
+      c.Ac[i] = ok ? gops[i] + ops_block(MP, OPS_H) : nullptr;
+      c.V[i] = ok ? blk(i, T_V) : nullptr; c.G2[i] = ok ? blk(i, T_G2) : nullptr;
+      c.b[i] = ok ? gops[i] + ops_alpha(MP) : nullptr;
+      c.beta[i] = ok ? ops[i] + ops_beta(MP) : nullptr;
+      c.dkl[i] = ok ? gops[i] + ops_scal(MP) + SC_KL : nullptr;
+      c.clamp_flag[i] = ok ? gops[i] + ops_scal(MP) + SC_CLAMP : nullptr;
+      c.N[i] = ok ? blk(i, T_NN) : nullptr; c.F[i] = ok ? blk(i, T_F) : nullptr;
+    }
+    MOBO_LAUNCH("combine_kernel", st, combine_kernel<<<dim3((MP2 + 255) / 256, nl), 256, 0, st>>>(c, MP));
+  }
+  // dP = W^T N W
+  mk(A, false, 2, [&](int i) { return ops[i] + ops_block(MP, OPS_WT); });
+  mk(B, false, 0, [&](int i) { return (const double*)blk(i, T_NN); });
+  outs(T_X1);
+  MOBO_TRY(gemm_batched(nl, MP, A, B, C, nullptr, 1.0, 0.0, nullptr, st));
+  mk(A, false, 0, [&](int i) { return (const double*)blk(i, T_X1); });
+  mk(B, false, 1, [&](int i) { return ops[i] + ops_block(MP, OPS_W); });
+  outs(T_DP);
+  MOBO_TRY(gemm_batched(nl, MP, A, B, C, nullptr, 1.0, 0.0, nullptr, st));
+  // dLq = tril(W^T F H) - g diag(1 / Lq_ii)
+  mk(A, false, 0, [&](int i) { return (const double*)blk(i, T_F); });
+  mk(B, false, 1, [&](int i) { return ops[i] + ops_block(MP, OPS_H); });
+  outs(T_X2);
+  MOBO_TRY(gemm_batched(nl, MP, A, B, C, nullptr, 1.0, 0.0, nullptr, st));
+  mk(A, false, 2, [&](int i) { return ops[i] + ops_block(MP, OPS_WT); });
+  mk(B, false, 0, [&](int i) { return (const double*)blk(i, T_X2); });
+  outs(T_Y2);
+  MOBO_TRY(gemm_batched(nl, MP, A, B, C, nullptr, 1.0, 0.0, nullptr, st));
+  {
+    DlqBatch q;
+    for (int i = 0; i < MAX_BATCH; ++i) {
+      const bool ok = i < nl;
+      q.E[i] = ok ? blk(i, T_Y2) : nullptr; q.LQ[i] = ok ? ops[i] + ops_block(MP, OPS_LQ) : nullptr;
+      q.dkl[i] = ok ? gops[i] + ops_scal(MP) + SC_KL : nullptr; q.dLq[i] = ok ? dLq[i] : nullptr;
+    }
+    MOBO_LAUNCH("dlq_extract_kernel", st,
+                dlq_extract_kernel<<<dim3((M * M + 255) / 256, nl), 256, 0, st>>>(q, M, MP));
+  }
+  // dm = W^T (b + g beta)
+  {
+    VecBatch v;
+    for (int i = 0; i < MAX_BATCH; ++i) {
+      const bool ok = i < nl;
+      v.WT[i] = ok ? ops[i] + ops_block(MP, OPS_WT) : nullptr;
+      v.b[i] = ok ? gops[i] + ops_alpha(MP) : nullptr;
+      v.beta[i] = ok ? ops[i] + ops_beta(MP) : nullptr;
+      v.dkl[i] = ok ? gops[i] + ops_scal(MP) + SC_KL : nullptr;
+      v.dm[i] = ok ? dm[i] : nullptr;
+    }
+    MOBO_LAUNCH("white_vec_kernel", st, white_vec_kernel<<<dim3((M + 7) / 8, nl), 256, 0, st>>>(v, M, MP));
+  }
+  // through K(Z, Z)
+  {
+    const int nblk = (M + KZB_WARPS - 1) / KZB_WARPS;
+    KzzBwdBatch o;
+    ReduceBatch r;
+    for (int i = 0; i < MAX_BATCH; ++i) {
+      const bool ok = i < nl;
+      o.dP[i] = ok ? blk(i, T_DP) : nullptr;
+      o.part_theta[i] = ok ? work[i] + T_N * MP2 : nullptr;
+      o.dzf[i] = (ok && dzf) ? dzf[i] : nullptr;
+      r.part[i] = o.part_theta[i];
+      r.out[i] = ok ? dtheta[i] : nullptr;
+      r.n[i] = ok ? theta_size(kinds[i], d) : 0;
+    }
+    MOBO_LAUNCH("kzz_bwd_kernel", st, kzz_bwd_kernel<<<dim3(nblk, nl), KZB_WARPS * 32, 0, st>>>(b, o));
+    MOBO_LAUNCH("reduce_batch_kernel", st, reduce_batch_kernel<<<dim3(1, nl), 32, 0, st>>>(r, nblk, KZB_NTH));
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 int mobo_layer_precompute(int kind, int d, int M, const double* Zx, const double* zf, const double* theta,
                           const double* m, const double* Lq, double jitter, double* ops, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  const int MP = padded(M);
-  if (d > kMaxD || MP > MAX_MP) return -2;
-  double* L = ops + ops_block(MP, OPS_L);
-  double* W = ops + ops_block(MP, OPS_W);
-  double* WT = ops + ops_block(MP, OPS_WT);
-  double* H = ops + ops_block(MP, OPS_H);
-  double* HT = ops + ops_block(MP, OPS_HT);
-  double* P = ops + ops_block(MP, OPS_P);
-  double* LQ = ops + ops_block(MP, OPS_LQ);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_done = true;
-  }
-  MOBO_TRY(mobo_kzz(kind, d, M, Zx, zf, theta, jitter, P, stream));
-  const size_t chol_smem = (size_t)(CH_NB * (CH_NB + 1) + 8 + (size_t)(MP - CH_NB) * CH_LDP) * sizeof(double);
-  MOBO_LAUNCH("chol_kernel", st, chol_kernel<<<1, CH_THREADS, chol_smem, st>>>(P, L, MP, ops + ops_scal(MP)));
-  const size_t tri_smem = (size_t)(MP / 32) * 32 * 36 * sizeof(double);
-  MOBO_LAUNCH("trtri_kernel", st, trtri_kernel<<<1, TI_THREADS, tri_smem, st>>>(L, W, MP));
-  MOBO_TRY(ew(EW_TRANSPOSE, M, MP, W, nullptr, WT, nullptr, 1.0, nullptr, nullptr, st));
-  MOBO_TRY(ew(EW_PAD_TRIL, M, MP, Lq, nullptr, LQ, nullptr, 1.0, nullptr, nullptr, st));
-  MOBO_TRY(gemm(MP, W, false, LQ, false, H, 1.0, 0.0, st));
-  MOBO_TRY(ew(EW_TRANSPOSE, M, MP, H, nullptr, HT, nullptr, 1.0, nullptr, nullptr, st));
-  MOBO_LAUNCH("finalize_kernel", st, finalize_kernel<<<1, 256, 0, st>>>(M, MP, m, ops));
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  return mobo_model_precompute(1, &kind, d, M, &Zx, &zf, &theta, &m, &Lq, jitter, &ops, stream);
 }
 
 int mobo_layer_precompute_bwd(int kind, int d, int M, const double* Zx, const double* zf, const double* theta,
                               const double* m, const double* Lq, const double* ops, const double* gops,
                               double* work, double* dtheta, double* dzf, double* dm, double* dLq, void* stream) {
-  (void)Lq;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int MP = padded(M);
-  if (d > kMaxD || MP > MAX_MP) return -2;
-  const size_t MP2 = (size_t)MP * MP;
-  const double* L = ops + ops_block(MP, OPS_L);
-  const double* W = ops + ops_block(MP, OPS_W);
-  const double* WT = ops + ops_block(MP, OPS_WT);
-  const double* H = ops + ops_block(MP, OPS_H);
-  const double* HT = ops + ops_block(MP, OPS_HT);
-  const double* LQ = ops + ops_block(MP, OPS_LQ);
-  const double* beta = ops + ops_beta(MP);
-  const double* A2 = gops + ops_block(MP, OPS_W);
-  const double* Ac = gops + ops_block(MP, OPS_H);
-  const double* dalpha = gops + ops_alpha(MP);
-  const double* dkl = gops + ops_scal(MP) + SC_KL;
-  double* T1 = work;
-  double* T2 = work + MP2;
-  double* T3 = work + 2 * MP2;
-  double* T4 = work + 3 * MP2;   // dH
-  double* T5 = work + 4 * MP2;   // dW
-  double* T6 = work + 5 * MP2;
-  double* dbeta = work + 6 * MP2;
-  double* mpad = dbeta + MP;     // m zero-padded to MP
-  double* part = mpad + MP;
-  // A1 = A2 - Ac  (gradient of the clamped first quadratic form)
-  MOBO_TRY(ew(EW_SUB, M, MP, A2, Ac, T1, nullptr, 1.0, nullptr, nullptr, st));
-  // Y = H^T W ; dY = 2 Y A2
-  MOBO_TRY(gemm(MP, HT, false, W, false, T2, 1.0, 0.0, st));
-  MOBO_TRY(gemm(MP, T2, false, A2, false, T3, 2.0, 0.0, st));
-  // dH = W dY^T + dkl H
-  MOBO_TRY(ew(EW_SCALE, M, MP, H, nullptr, T4, dkl, 1.0, nullptr, nullptr, st));
-  MOBO_TRY(gemm(MP, W, false, T3, true, T4, 1.0, 1.0, st));
-  // dbeta = W dalpha + dkl beta ; dm = W^T dbeta
-  MOBO_LAUNCH("dbeta_kernel", st, dbeta_kernel<<<1, 256, 0, st>>>(M, MP, ops, dalpha, dkl, dbeta, dm));
-  cudaMemsetAsync(mpad, 0, sizeof(double) * MP, st);
-  cudaMemcpyAsync(mpad, m, sizeof(double) * M, cudaMemcpyDeviceToDevice, st);
-  // dW = -2 W A1 + H dY + beta dalpha^T + dbeta m^T + dH Lq^T   (lower triangle kept)
-  MOBO_TRY(gemm(MP, W, false, T1, false, T5, -2.0, 0.0, st));
-  MOBO_TRY(gemm(MP, H, false, T3, false, T5, 1.0, 1.0, st));
-  MOBO_TRY(ew(EW_RANK1_ADD, M, MP, nullptr, nullptr, T5, nullptr, 1.0, beta, dalpha, st));
-  MOBO_TRY(ew(EW_RANK1_ADD, M, MP, nullptr, nullptr, T5, nullptr, 1.0, dbeta, mpad, st));
-  MOBO_TRY(gemm(MP, T4, false, LQ, true, T5, 1.0, 1.0, st));
-  MOBO_TRY(ew(EW_TRIL_INPLACE, M, MP, T5, nullptr, T5, nullptr, 1.0, nullptr, nullptr, st));
-  // dLq = tril(W^T dH) - dkl diag(1 / Lq_ii)
-  MOBO_TRY(gemm(MP, WT, false, T4, false, T6, 1.0, 0.0, st));
-  MOBO_LAUNCH("dlq_extract_kernel", st, dlq_extract_kernel<<<(M * M + 255) / 256, 256, 0, st>>>(M, MP, T6, LQ, dkl, dLq));
-  // dL = -tril(W^T dW W^T) + dkl diag(1 / L_ii)
-  MOBO_TRY(gemm(MP, WT, false, T5, false, T1, 1.0, 0.0, st));
-  MOBO_TRY(gemm(MP, T1, false, WT, false, T2, 1.0, 0.0, st));
-  MOBO_TRY(ew(EW_NEG_TRIL_DIAG, M, MP, T2, L, T3, dkl, 1.0, nullptr, nullptr, st));
-  // dP = sym( W^T Phi(L^T dL) W )
-  MOBO_TRY(gemm(MP, L, true, T3, false, T1, 1.0, 0.0, st));
-  MOBO_TRY(ew(EW_PHI, M, MP, T1, nullptr, T2, nullptr, 1.0, nullptr, nullptr, st));
-  MOBO_TRY(gemm(MP, WT, false, T2, false, T1, 1.0, 0.0, st));
-  MOBO_TRY(gemm(MP, T1, false, W, false, T2, 1.0, 0.0, st));
-  MOBO_TRY(ew(EW_SYM, M, MP, T2, nullptr, T3, nullptr, 1.0, nullptr, nullptr, st));
-  // through K(Z, Z)
-  const int nblk = (M + KZB_WARPS - 1) / KZB_WARPS;
-  MOBO_LAUNCH("kzz_bwd_kernel", st, kzz_bwd_kernel<<<nblk, KZB_WARPS * 32, 0, st>>>(kind, d, M, MP, Zx, zf, theta, T3, part, dzf, 0));
-  MOBO_TRY(launch_reduce_partials(part, nblk, theta_size(kind, d), 5 + 2 * kMaxD, dtheta, 0, st));
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  return mobo_model_precompute_bwd(1, &kind, d, M, &Zx, &zf, &theta, &m, &Lq, &ops, &gops, &work, &dtheta, &dzf, &dm,
+                                   &dLq, stream);
 }
 
 static void fill_row_args(RowArgs& a, int kind, int d, int M, const double* Zx, const double* zf,
@@ -173,7 +252,7 @@ static void fill_row_args(RowArgs& a, int kind, int d, int M, const double* Zx, 
   a.mu_prev = mu_prev; a.var_prev = var_prev; a.prep = prep < 1 ? 1 : prep;
   a.eps = eps; a.eps_mod = eps_mod < 1 ? 1 : eps_mod; a.f_direct = f_direct; a.R = R; a.training = training;
   a.mu = nullptr; a.var = nullptr; a.craw = nullptr; a.clamp_count = nullptr;
-  a.Ksave = nullptr; a.Tsave = nullptr; a.Usave = nullptr;
+  a.Tsave = nullptr; a.Usave = nullptr;
   a.dmu = nullptr; a.dvar = nullptr; a.df = nullptr; a.dxrow = nullptr; a.part_theta = nullptr; a.part_zf = nullptr;
   a.want_param_grads = 0; a.want_x_grads = 0;
 }
@@ -182,12 +261,12 @@ int mobo_layer_rows_fwd(int kind, int d, int M, const double* Zx, const double* 
                         const double* ops, const double* x, int xrep, const double* mu_prev, const double* var_prev,
                         int prep, const double* eps, long long eps_mod, const double* f_direct, long long R,
                         int training, double* mu, double* var, double* craw, unsigned int* clamp_count,
-                        double* Ksave, double* Tsave, double* Usave, void* stream) {
+                        double* Tsave, double* Usave, void* stream) {
   RowArgs a;
   fill_row_args(a, kind, d, M, Zx, zf, theta, ops, x, xrep, mu_prev, var_prev, prep, eps, eps_mod, f_direct, R,
                 training);
   a.mu = mu; a.var = var; a.craw = craw; a.clamp_count = clamp_count;
-  a.Ksave = Ksave; a.Tsave = Tsave; a.Usave = Usave;
+  a.Tsave = Tsave; a.Usave = Usave;
   return launch_row_fwd(a, (cudaStream_t)stream);
 }
 
@@ -195,7 +274,7 @@ int mobo_layer_rows_bwd(int kind, int d, int M, const double* Zx, const double* 
                         const double* ops, const double* x, int xrep, const double* mu_prev, const double* var_prev,
                         int prep, const double* eps, long long eps_mod, const double* f_direct, long long R,
                         int training, const double* dmu, const double* dvar, const double* craw,
-                        const unsigned int* clamp_count, const double* Ksave, const double* Tsave,
+                        const unsigned int* clamp_count, const double* Tsave,
                         const double* Usave, int want_param_grads, double* df, double* dxrow, double* dtheta,
                         double* dzf, double* gops, double* work, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -220,10 +299,11 @@ int mobo_layer_rows_bwd(int kind, int d, int M, const double* Zx, const double* 
     if (kind == 1 && dzf) MOBO_TRY(launch_reduce_partials(part_zf, grid, M, MP, dzf, 0, st));
   }
   if (gops) {
-    MOBO_TRY(launch_syrk(Ksave, dvar, craw, 0, MP, R, part_syrk, gops + ops_block(MP, OPS_W), clamp_count, dmu,
-                         part_alpha, gops + ops_alpha(MP), st));
-    MOBO_TRY(launch_syrk(Ksave, dvar, craw, 1, MP, R, part_syrk, gops + ops_block(MP, OPS_H),
-                         training ? clamp_count : nullptr, nullptr, nullptr, nullptr, st));
+    MOBO_TRY(launch_syrk(Tsave, dvar, craw, 0, MP, R, part_syrk, gops + ops_block(MP, OPS_W), clamp_count, dmu,
+                         part_alpha, gops + ops_alpha(MP), nullptr, st));
+    MOBO_TRY(launch_syrk(Tsave, dvar, craw, 1, MP, R, part_syrk, gops + ops_block(MP, OPS_H),
+                         training ? clamp_count : nullptr, nullptr, nullptr, nullptr,
+                         gops + ops_scal(MP) + SC_CLAMP, st));
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

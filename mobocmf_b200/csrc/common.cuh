@@ -41,18 +41,21 @@ constexpr int kMaxD = 8;               // max number of x columns (ARD dims) han
 constexpr double kMinVariance = 1e-10; // gpytorch settings.min_variance (fp64), quirk Q9
 
 // ---- operator buffer layout (doubles), one per (model, layer); MP = M rounded up to a multiple of 32 ----
-// [L | W | WT | H | HT | P | LQ]  seven MP x MP row-major blocks, then beta[MP], alpha[MP], scal[16]
+// [L | W | WT | H | HT | P | LQ]  seven MP x MP row-major blocks, then beta[MP], alpha[MP], scal[16], rowstat[4 MP]
 //   L = chol(K_zz + jitter I), W = L^-1, WT = W^T, H = W tril(L_q), HT = H^T, P = K_zz + jitter I, LQ = tril(L_q)
 // The GRADIENT buffer of an operator buffer has the same layout and carries, by convention of this library,
-//   block OPS_W: A2 = sum_r dvar_r k_r k_r^T,  block OPS_H: Ac = same over clamped rows only,
-//   alpha slot: dalpha = sum_r dmu_r k_r,  scal[SC_KL]: d loss / d KL;  every other entry is ignored.
+//   block OPS_W: A2 = sum_r dvar_r t_r t_r^T (t = W k),  block OPS_H: Ac = same over clamped rows only,
+//   alpha slot: b = sum_r dmu_r t_r,  scal[SC_KL]: d loss / d KL, scal[SC_CLAMP]: #clamped rows;  rest ignored.
 enum OpsBlock { OPS_L = 0, OPS_W = 1, OPS_WT = 2, OPS_H = 3, OPS_HT = 4, OPS_P = 5, OPS_LQ = 6, OPS_NBLOCKS = 7 };
-enum OpsScal { SC_KL = 0, SC_LOGDET_P = 1, SC_LOGDET_Q = 2, SC_BETA2 = 3, SC_H2 = 4, SC_STATUS = 5 };
+// scal[SC_CLAMP] is meaningful in the GRADIENT buffer: number of clamped rows behind block OPS_H (0 -> Ac == 0)
+enum OpsScal { SC_KL = 0, SC_LOGDET_P = 1, SC_LOGDET_Q = 2, SC_BETA2 = 3, SC_H2 = 4, SC_STATUS = 5, SC_CLAMP = 6,
+               SC_COUNTER = 8 };
 __host__ __device__ inline size_t ops_block(int MP, int b) { return (size_t)b * MP * MP; }
 __host__ __device__ inline size_t ops_beta(int MP) { return (size_t)OPS_NBLOCKS * MP * MP; }
 __host__ __device__ inline size_t ops_alpha(int MP) { return (size_t)OPS_NBLOCKS * MP * MP + MP; }
 __host__ __device__ inline size_t ops_scal(int MP) { return (size_t)OPS_NBLOCKS * MP * MP + 2 * MP; }
-__host__ __device__ inline size_t ops_size(int MP) { return (size_t)OPS_NBLOCKS * MP * MP + 2 * MP + 16; }
+__host__ __device__ inline size_t ops_rowstat(int MP) { return (size_t)OPS_NBLOCKS * MP * MP + 2 * MP + 16; }
+__host__ __device__ inline size_t ops_size(int MP) { return (size_t)OPS_NBLOCKS * MP * MP + 6 * MP + 16; }
 
 // D(8x8) += A(8x4, row) * B(4x8, col).  lane = 4*g + t:  A[g][t], B[t][g], C[g][2t..2t+1].
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {

@@ -1,29 +1,55 @@
-// Per-step M x M operator chain of one sparse-GP layer (forward and backward) for sm_100a.
+// Per-step M x M operator chain of the sparse-GP layers (forward and backward) for sm_100a, batched over layers.
 //
 // Forward (what the reference reaches through UnwhitenedVariationalStrategy.forward / kl_mvn_mvn [upstream gpytorch],
 // called from mobocmf/layers/mfdgp_hidden_layer.py:286 and mobocmf/mlls/variational_elbo_mf.py:40):
 //   P = K(Z_l, Z_l) + jitter I      (CovarianceMatrixMF.add_jitter, layers/mfdgp_hidden_layer.py:17-20)
-//   L = chol(P);  W = L^-1;  H = W tril(L_q);  beta = W m;  alpha = W^T beta
+//   L = chol(P);  W = L^-1;  H = W tril(L_q);  beta = W m
 //   KL = 1/2 [ 2 sum log L_ii - sum log L_q,ii^2 + |beta|^2 + |H|_F^2 - M ]
-// Backward: from the row pass's second-order statistics (A2 = sum dvar k k^T, Ac = clamped-row part, dalpha) and
-// dKL to d m, d L_q, d theta, d zf (the gradient through the inducing inputs [Z, m_{l-1}]).
+// Backward: the loss depends on P only through P^-1 = W^T W and P^-1 S P^-1 = W^T G2 W (G2 = H H^T), so with the
+// row pass's WHITENED statistics A2 = sum dvar t t^T (A1 = A2 minus the clamped rows), b = sum dmu t (t = W k) and
+// g = dLoss/dKL everything is assembled in whitened space (moderate magnitudes) and mapped back by one congruence:
+//   dP  = W^T [ A1 - A2 G2 - G2 A2 - 1/2 (beta b^T + b beta^T) + g/2 (I - beta beta^T - G2) ] W
+//   dLq = tril(W^T (2 A2 + g I) H) - g diag(1 / L_q,ii),      dm = W^T (b + g beta)
+// (no differentiation through the Cholesky factor is needed), then dP goes through K(Z,Z) to d theta and d zf —
+// the gradient through the inducing inputs [Z, m_{l-1}].
 //
 // All matrices are MP x MP row-major (MP = M rounded up to 32, identity/zero padded) and L2-resident; products run
-// on the DMMA pipe through one strided 64x64-tile kernel.
+// on the DMMA pipe.  The layers of a model are independent here and are batched in the grid.
 #include "common.cuh"
 
 namespace mobo {
 
-constexpr int MAX_MP_FINAL = 256;
+constexpr int MAX_BATCH = 8;
+
+struct LayerBatch {
+  int n;
+  int d, M, MP;
+  int kind[MAX_BATCH];
+  const double* Zx[MAX_BATCH];
+  const double* zf[MAX_BATCH];
+  const double* theta[MAX_BATCH];
+  const double* m[MAX_BATCH];
+  const double* Lq[MAX_BATCH];
+  double* ops[MAX_BATCH];
+};
+
+struct PtrBatch3 {
+  const double* A[MAX_BATCH];
+  const double* B[MAX_BATCH];
+  double* C[MAX_BATCH];
+  double* Ct[MAX_BATCH];   // optional transposed copy of C
+};
 
 // ---------------------------------------------------------------------------------------------------
 // covariance function between inducing inputs
 // ---------------------------------------------------------------------------------------------------
-__global__ void kzz_kernel(int kind, int d, int M, int MP, const double* __restrict__ Zx,
-                           const double* __restrict__ zf, const double* __restrict__ theta, double jitter,
-                           double* __restrict__ P) {
+__global__ void kzz_kernel(LayerBatch b, double jitter, int block_index /* which ops block receives P */) {
   __shared__ KernParams kp;
-  if (threadIdx.x == 0) load_kern_params(kp, kind, d, theta);
+  const int bi = blockIdx.y;
+  const int kind = b.kind[bi], d = b.d, M = b.M, MP = b.MP;
+  const double* Zx = b.Zx[bi];
+  const double* zf = b.zf[bi];
+  if (threadIdx.x == 0) load_kern_params(kp, kind, d, b.theta[bi]);
   __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= MP * MP) return;
@@ -48,22 +74,27 @@ __global__ void kzz_kernel(int kind, int d, int M, int MP, const double* __restr
       val = kp.a1 * E1 * (kp.vlin * fi * fj + kp.af * exp(-0.5 * dff * dff * kp.ilf)) + kp.a2 * exp(-0.5 * D2);
     }
   }
-  P[idx] = val;
+  (b.ops[bi] + ops_block(MP, block_index))[idx] = val;
 }
 
 // backward through K(Z,Z): dP symmetric.  One warp per inducing point i.
-//   dtheta += sum_ij dP_ij dk_ij/dtheta ;  dzf_i += 2 sum_j dP_ij dk(z_i,z_j)/d f_i
+//   dtheta += sum_ij dP_ij dk_ij/dtheta ;  dzf_i = 2 sum_j dP_ij dk(z_i,z_j)/d f_i
 constexpr int KZB_WARPS = 8;
-__global__ void __launch_bounds__(KZB_WARPS * 32) kzz_bwd_kernel(int kind, int d, int M, int MP,
-                                                                 const double* __restrict__ Zx,
-                                                                 const double* __restrict__ zf,
-                                                                 const double* __restrict__ theta,
-                                                                 const double* __restrict__ dP,
-                                                                 double* __restrict__ part_theta,   // [grid][5+2*kMaxD]
-                                                                 double* __restrict__ dzf_out, int accumulate_zf) {
+constexpr int KZB_NTH = 5 + 2 * kMaxD;
+struct KzzBwdBatch {
+  const double* dP[MAX_BATCH];
+  double* part_theta[MAX_BATCH];   // [gridDim.x][KZB_NTH]
+  double* dzf[MAX_BATCH];
+};
+__global__ void __launch_bounds__(KZB_WARPS * 32) kzz_bwd_kernel(LayerBatch b, KzzBwdBatch o) {
   __shared__ KernParams kp;
-  __shared__ double accw[KZB_WARPS][5 + 2 * kMaxD];
-  if (threadIdx.x == 0) load_kern_params(kp, kind, d, theta);
+  __shared__ double accw[KZB_WARPS][KZB_NTH];
+  const int bi = blockIdx.y;
+  const int kind = b.kind[bi], d = b.d, M = b.M, MP = b.MP;
+  const double* Zx = b.Zx[bi];
+  const double* zf = b.zf[bi];
+  const double* dP = o.dP[bi];
+  if (threadIdx.x == 0) load_kern_params(kp, kind, d, b.theta[bi]);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * KZB_WARPS + warp;
@@ -75,6 +106,9 @@ __global__ void __launch_bounds__(KZB_WARPS * 32) kzz_bwd_kernel(int kind, int d
   double dzi = 0.0;
   if (i < M) {
     const double fi = kind == 1 ? zf[i] : 0.0;
+    double zi[kMaxD];
+#pragma unroll
+    for (int c = 0; c < kMaxD; ++c) zi[c] = c < d ? Zx[(size_t)i * d + c] : 0.0;
     for (int j = lane; j < M; j += 32) {
       const double gk = dP[(size_t)i * MP + j];
       if (i == j) {
@@ -92,7 +126,7 @@ __global__ void __launch_bounds__(KZB_WARPS * 32) kzz_bwd_kernel(int kind, int d
       double D1 = 0.0, D2 = 0.0, diff[kMaxD];
 #pragma unroll
       for (int c = 0; c < kMaxD; ++c) {
-        diff[c] = c < d ? Zx[(size_t)i * d + c] - Zx[(size_t)j * d + c] : 0.0;
+        diff[c] = c < d ? zi[c] - Zx[(size_t)j * d + c] : 0.0;
         D1 = fma(diff[c] * diff[c], kp.il1[c], D1);
         D2 = fma(diff[c] * diff[c], kp.il2[c], D2);
       }
@@ -125,7 +159,7 @@ __global__ void __launch_bounds__(KZB_WARPS * 32) kzz_bwd_kernel(int kind, int d
     }
   }
   dzi = warp_sum(dzi);
-  if (lane == 0 && i < M && kind == 1) dzf_out[i] = (accumulate_zf ? dzf_out[i] : 0.0) + 2.0 * dzi;
+  if (lane == 0 && i < M && kind == 1 && o.dzf[bi]) o.dzf[bi][i] = 2.0 * dzi;
 #pragma unroll
   for (int q = 0; q < 5; ++q) {
     const double s = warp_sum(th_s[q]);
@@ -140,7 +174,7 @@ __global__ void __launch_bounds__(KZB_WARPS * 32) kzz_bwd_kernel(int kind, int d
   }
   __syncthreads();
   const int tid = threadIdx.x;
-  if (tid < 5 + 2 * kMaxD) {
+  if (tid < KZB_NTH) {
     double s = 0.0;
     for (int w = 0; w < KZB_WARPS; ++w) s += accw[w][tid];
     double out = 0.0;
@@ -157,78 +191,142 @@ __global__ void __launch_bounds__(KZB_WARPS * 32) kzz_bwd_kernel(int kind, int d
         out = s * kp.il2[c] * sqrt(kp.il2[c]);
       }
     }
-    if (slot >= 0) part_theta[(size_t)blockIdx.x * (5 + 2 * kMaxD) + slot] = out;
+    if (slot >= 0) o.part_theta[bi][(size_t)blockIdx.x * KZB_NTH + slot] = out;
   }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Cholesky  L = chol(P)   (blocked right-looking, one CTA per matrix, operands stay in L2)
-// ---------------------------------------------------------------------------------------------------
-constexpr int CH_NB = 32, CH_THREADS = 1024, CH_LDP = 36;
+// out[bi][i] = sum_b part[bi][b][i]  (fixed order)
+struct ReduceBatch { const double* part[MAX_BATCH]; double* out[MAX_BATCH]; int n[MAX_BATCH]; };
+__global__ void reduce_batch_kernel(ReduceBatch r, int nblocks, int stride) {
+  const int bi = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= r.n[bi]) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += r.part[bi][(size_t)b * stride + i];
+  r.out[bi][i] = s;
+}
 
-__global__ void __launch_bounds__(CH_THREADS, 1) chol_kernel(const double* __restrict__ P, double* __restrict__ L,
-                                                            int MP, double* __restrict__ scal) {
+// ---------------------------------------------------------------------------------------------------
+// L = chol(P) and W = L^-1 (also W^T) in one CTA per matrix; operands stay in L2, panels in shared memory.
+// Blocked right-looking Cholesky (NB = 32): the diagonal block is factorised and inverted in registers by one warp
+// (lane = row, columns exchanged by shuffles), the panel is A D^-T and the trailing update is a DMMA SYRK.  The
+// inverse reuses the inverted diagonal blocks and fills the block diagonals in order of increasing distance:
+// W_ik = -W_ii (sum_{j=k}^{i-1} L_ij W_jk).
+// ---------------------------------------------------------------------------------------------------
+constexpr int CH_NB = 32, CH_THREADS = 512, CH_WARPS = CH_THREADS / 32, CH_LD = 36;
+
+__device__ __forceinline__ void chol32_inwarp(double (&row)[32], int lane, int& fail) {
+  // row[c] = A[lane][c] (lower part valid).  On exit row[c] = L[lane][c] for c <= lane.
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const double djj = __shfl_sync(0xffffffffu, row[j], j);
+    if (!(djj > 0.0)) fail = 1;
+    const double ljj = sqrt(djj);
+    if (lane == j) row[j] = ljj;
+    else if (lane > j) row[j] = row[j] / ljj;
+#pragma unroll
+    for (int c = j + 1; c < 32; ++c) {
+      const double lcj = __shfl_sync(0xffffffffu, row[j], c);   // L[c][j]
+      if (lane >= c) row[c] = fma(-row[j], lcj, row[c]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) chol_inv_kernel(LayerBatch b) {
   extern __shared__ __align__(16) double sh[];
-  double (*D)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(sh);
-  double* panel = sh + CH_NB * (CH_NB + 1) + 8;   // [(MP-32)][CH_LDP]
-  __shared__ int fail;
+  const int MP = b.MP;
+  double* ops = b.ops[blockIdx.x];
+  const double* P = ops + ops_block(MP, OPS_P);
+  double* L = ops + ops_block(MP, OPS_L);
+  double* W = ops + ops_block(MP, OPS_W);
+  double* WT = ops + ops_block(MP, OPS_WT);
+  double* D = sh;                         // [32][CH_LD]   factor of the current diagonal block
+  double* Dinv = sh + 32 * CH_LD;         // [32][CH_LD]   its inverse
+  double* panel = sh + 64 * CH_LD;        // [(MP-32)][CH_LD]  (also S scratch of the inverse phases)
+  __shared__ int fail_flag;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  if (tid == 0) fail = 0;
+  const int nb = MP / CH_NB;
+  if (tid == 0) fail_flag = 0;
   for (int idx = tid; idx < MP * MP; idx += CH_THREADS) {
     const int i = idx / MP, j = idx - i * MP;
     L[idx] = j <= i ? P[idx] : 0.0;
+    W[idx] = 0.0;
   }
   __syncthreads();
-  for (int k0 = 0; k0 < MP; k0 += CH_NB) {
-    D[tid >> 5][tid & 31] = L[(size_t)(k0 + (tid >> 5)) * MP + k0 + (tid & 31)];
-    __syncthreads();
+  for (int kb = 0; kb < nb; ++kb) {
+    const int k0 = kb * CH_NB;
     if (warp == 0) {
-      for (int j = 0; j < CH_NB; ++j) {
-        const double djj = D[j][j];
-        if (!(djj > 0.0)) { if (lane == 0) fail = 1; }
-        const double ljj = sqrt(djj);
-        if (lane == j) D[j][j] = ljj;
-        if (lane > j) D[lane][j] = D[lane][j] / ljj;
-        __syncwarp();
-        if (lane > j) {
-          const double lij = D[lane][j];
-          for (int c = j + 1; c <= lane; ++c) D[lane][c] -= lij * D[c][j];
-        }
-        __syncwarp();
+      double row[32];
+      const double* src = L + (size_t)(k0 + lane) * MP + k0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) row[c] = src[c];
+      int fail = 0;
+      chol32_inwarp(row, lane, fail);
+      if (fail) fail_flag = 1;
+      double* dst = L + (size_t)(k0 + lane) * MP + k0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const double v = c <= lane ? row[c] : 0.0;
+        dst[c] = v;
+        D[lane * CH_LD + c] = v;
+      }
+      __syncwarp();
+      // inverse of the lower-triangular block: lane = column c, forward substitution down the rows
+      double x[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) s = fma(-D[i * CH_LD + k], x[k], s);
+        x[i] = (i >= lane) ? s / D[i * CH_LD + i] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        Dinv[i * CH_LD + lane] = x[i];
+        W[(size_t)(k0 + i) * MP + k0 + lane] = x[i];
       }
     }
     __syncthreads();
-    {
-      const int i = tid >> 5, j = tid & 31;
-      L[(size_t)(k0 + i) * MP + k0 + j] = j <= i ? D[i][j] : 0.0;
-    }
     const int nrows = MP - k0 - CH_NB;
     if (nrows > 0) {
-      // panel: X D^T = A  -> forward substitution along each row
-      if (tid < nrows) {
-        double x[CH_NB];
-        const double* arow = L + (size_t)(k0 + CH_NB + tid) * MP + k0;
+      // panel X = A Dinv^T : warp items of 16 rows x 32 cols
+      for (int item = warp; item < nrows / 16; item += CH_WARPS) {
+        const int r0 = item * 16;
+        double acc[2][4][2];
 #pragma unroll
-        for (int c = 0; c < CH_NB; ++c) x[c] = arow[c];
+        for (int x = 0; x < 2; ++x)
 #pragma unroll
-        for (int c = 0; c < CH_NB; ++c) {
-          double s = x[c];
+          for (int y = 0; y < 4; ++y) { acc[x][y][0] = 0.0; acc[x][y][1] = 0.0; }
+        const double* Arow = L + (size_t)(k0 + CH_NB + r0) * MP + k0;
 #pragma unroll
-          for (int k = 0; k < c; ++k) s = fma(-x[k], D[c][k], s);
-          x[c] = s / D[c][c];
+        for (int kk = 0; kk < CH_NB; kk += 4) {
+          double af[2], bf[4];
+#pragma unroll
+          for (int x = 0; x < 2; ++x) af[x] = Arow[(size_t)(8 * x + g) * MP + kk + t];
+#pragma unroll
+          for (int y = 0; y < 4; ++y) bf[y] = Dinv[(8 * y + g) * CH_LD + kk + t];   // B[k][n] = Dinv[n][k]
+#pragma unroll
+          for (int x = 0; x < 2; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
         }
-        double* orow = L + (size_t)(k0 + CH_NB + tid) * MP + k0;
+        __syncwarp();
 #pragma unroll
-        for (int c = 0; c < CH_NB; ++c) {
-          orow[c] = x[c];
-          panel[(size_t)tid * CH_LDP + c] = x[c];
-        }
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int rr = r0 + 8 * x + g, cc = 8 * y + 2 * t + e;
+              panel[(size_t)rr * CH_LD + cc] = acc[x][y][e];
+              L[(size_t)(k0 + CH_NB + rr) * MP + k0 + cc] = acc[x][y][e];
+            }
       }
       __syncthreads();
-      // trailing update: L[i][j] -= panel[i] . panel[j]  on 32x32 blocks (bi >= bj), DMMA
+      // trailing update: L[i][j] -= panel[i] . panel[j]  on 32x32 blocks (bi >= bj)
       const int nblk = nrows / CH_NB, nb2 = nblk * (nblk + 1) / 2;
-      for (int blk = warp; blk < nb2; blk += CH_THREADS / 32) {
+      for (int blk = warp; blk < nb2; blk += CH_WARPS) {
         int bi = 0, rem = blk;
         while (rem > bi) { rem -= bi + 1; ++bi; }
         const int bj = rem;
@@ -241,9 +339,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_kernel(const double* __res
         for (int kk = 0; kk < CH_NB; kk += 4) {
           double af[4], bf[4];
 #pragma unroll
-          for (int x = 0; x < 4; ++x) af[x] = panel[(size_t)(bi * CH_NB + 8 * x + g) * CH_LDP + kk + t];
+          for (int x = 0; x < 4; ++x) af[x] = panel[(size_t)(bi * CH_NB + 8 * x + g) * CH_LD + kk + t];
 #pragma unroll
-          for (int y = 0; y < 4; ++y) bf[y] = panel[(size_t)(bj * CH_NB + 8 * y + g) * CH_LDP + kk + t];
+          for (int y = 0; y < 4; ++y) bf[y] = panel[(size_t)(bj * CH_NB + 8 * y + g) * CH_LD + kk + t];
 #pragma unroll
           for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -263,45 +361,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_kernel(const double* __res
     }
     __syncthreads();
   }
-  if (tid == 0) scal[SC_STATUS] = fail ? 1.0 : 0.0;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// W = L^-1  (blocked, one CTA per matrix): diagonal 32x32 blocks by substitution, then block diagonals
-// W_ik = -W_ii (sum_{j=k}^{i-1} L_ij W_jk) in order of increasing distance i-k, DMMA products.
-// ---------------------------------------------------------------------------------------------------
-constexpr int TI_THREADS = 1024;
-__global__ void __launch_bounds__(TI_THREADS, 1) trtri_kernel(const double* __restrict__ L, double* __restrict__ W,
-                                                             int MP) {
-  extern __shared__ __align__(16) double sh[];
-  const int nb = MP / 32;
-  double* Sblk = sh;                       // [nb][32][36]  S = sum_j L_ij W_jk  per block of the current diagonal
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  for (int idx = tid; idx < MP * MP; idx += TI_THREADS) W[idx] = 0.0;
-  __syncthreads();
-  // diagonal blocks: lane = column c of the block, solve L_bb x = e_c
-  if (warp < nb) {
-    const int b = warp, c = lane;
-    const double* Lb = L + (size_t)(32 * b) * MP + 32 * b;
-    double x[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      double s = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < i; ++k) s = fma(-__ldg(Lb + (size_t)i * MP + k), x[k], s);
-      x[i] = (i >= c) ? s / __ldg(Lb + (size_t)i * MP + i) : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) W[(size_t)(32 * b + i) * MP + 32 * b + c] = x[i];
-  }
-  __threadfence_block();
-  __syncthreads();
+  // ---- W = L^-1: block diagonals of increasing distance; 4 warps per 32x32 block (16x16 quadrants) ----
+  double* Sblk = panel;                    // [nb][32][CH_LD]
   for (int dd = 1; dd < nb; ++dd) {
     const int nblocks = nb - dd;
-    // 4 warps per block, each a 16x16 quadrant of the 32x32 block
-    // phase A: S = sum_j L_ij W_jk
-    for (int item = warp; item < nblocks * 4; item += TI_THREADS / 32) {
+    for (int item = warp; item < nblocks * 4; item += CH_WARPS) {
       const int bq = item >> 2, q = item & 3;
       const int k = bq, i = bq + dd;
       const int r0 = 16 * (q >> 1), c0 = 16 * (q & 1);
@@ -322,22 +386,21 @@ __global__ void __launch_bounds__(TI_THREADS, 1) trtri_kernel(const double* __re
             for (int y = 0; y < 2; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
         }
       }
-      double* S = Sblk + (size_t)bq * 32 * 36;
+      double* S = Sblk + (size_t)bq * 32 * CH_LD;
 #pragma unroll
       for (int x = 0; x < 2; ++x)
 #pragma unroll
         for (int y = 0; y < 2; ++y)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) S[(size_t)(r0 + 8 * x + g) * 36 + c0 + 8 * y + 2 * t + e] = acc[x][y][e];
+          for (int e = 0; e < 2; ++e) S[(size_t)(r0 + 8 * x + g) * CH_LD + c0 + 8 * y + 2 * t + e] = acc[x][y][e];
     }
     __syncthreads();
-    // phase B: W_ik = -W_ii S
-    for (int item = warp; item < nblocks * 4; item += TI_THREADS / 32) {
+    for (int item = warp; item < nblocks * 4; item += CH_WARPS) {
       const int bq = item >> 2, q = item & 3;
       const int k = bq, i = bq + dd;
       const int r0 = 16 * (q >> 1), c0 = 16 * (q & 1);
       const double* Wii = W + (size_t)(32 * i) * MP + 32 * i;
-      const double* S = Sblk + (size_t)bq * 32 * 36;
+      const double* S = Sblk + (size_t)bq * 32 * CH_LD;
       double acc[2][2][2] = {};
 #pragma unroll
       for (int kk = 0; kk < 32; kk += 4) {
@@ -345,7 +408,7 @@ __global__ void __launch_bounds__(TI_THREADS, 1) trtri_kernel(const double* __re
 #pragma unroll
         for (int x = 0; x < 2; ++x) af[x] = Wii[(size_t)(r0 + 8 * x + g) * MP + kk + t];
 #pragma unroll
-        for (int y = 0; y < 2; ++y) bf[y] = S[(size_t)(kk + t) * 36 + c0 + 8 * y + g];
+        for (int y = 0; y < 2; ++y) bf[y] = S[(size_t)(kk + t) * CH_LD + c0 + 8 * y + g];
 #pragma unroll
         for (int x = 0; x < 2; ++x)
 #pragma unroll
@@ -362,196 +425,252 @@ __global__ void __launch_bounds__(TI_THREADS, 1) trtri_kernel(const double* __re
     __threadfence_block();
     __syncthreads();
   }
+  for (int idx = tid; idx < MP * MP; idx += CH_THREADS) {
+    const int i = idx / MP, j = idx - i * MP;
+    WT[idx] = W[(size_t)j * MP + i];
+  }
+  if (tid == 0) (ops + ops_scal(MP))[SC_STATUS] = fail_flag ? 1.0 : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// strided small GEMM:  C = alpha * op(A) op(B) + beta * C   (n x n x n, n = MP multiple of 32), 64x64 tiles
+// batched strided GEMM  C = alpha op(A) op(B) + beta C  (n x n x n, n multiple of 32), 32x32 tiles, BK = 32,
+// register-prefetched double buffering.  Triangular operands shorten the k range:
+//   a_tri: 1 = op(A)[m][k] == 0 for k > m (lower), 2 = == 0 for k < m (upper);  b_tri likewise on op(B)[k][n]:
+//   1 = lower (== 0 for n > k), 2 = upper (== 0 for n < k).
 // element (m,k) of op(A) = A[m*rsA + k*csA];  element (k,n) of op(B) = B[k*rsB + n*csB]
 // ---------------------------------------------------------------------------------------------------
-constexpr int GM_T = 64, GM_K = 16, GM_THREADS = 256;
-__global__ void __launch_bounds__(GM_THREADS) gemm_kernel(int n, const double* __restrict__ A, int rsA, int csA,
-                                                         const double* __restrict__ B, int rsB, int csB,
-                                                         double* __restrict__ C, double alpha, double beta) {
-  __shared__ double As[GM_K][GM_T + 4];
-  __shared__ double Bs[GM_K][GM_T + 4];
+constexpr int GM_T = 32, GM_K = 32, GM_THREADS = 128, GM_LD = GM_T + 4;
+
+struct GemmArgs {
+  int n;
+  int rsA, csA, rsB, csB;
+  int a_tri, b_tri;
+  double alpha, beta;
+  const double* skip_if_zero[MAX_BATCH];   // optional per-entry device flag: skip the entry when *flag == 0
+  PtrBatch3 p;
+};
+
+__global__ void __launch_bounds__(GM_THREADS) gemm_kernel(const __grid_constant__ GemmArgs a) {
+  if (a.skip_if_zero[blockIdx.z] && *a.skip_if_zero[blockIdx.z] == 0.0) return;
+  __shared__ double As[2][GM_K][GM_LD];   // [k][m]
+  __shared__ double Bs[2][GM_K][GM_LD];   // [k][n]
+  const int bi = blockIdx.z;
+  const double* __restrict__ A = a.p.A[bi];
+  const double* __restrict__ B = a.p.B[bi];
+  double* __restrict__ C = a.p.C[bi];
+  double* __restrict__ Ct = a.p.Ct[bi];
+  const int n = a.n;
   const int m0 = blockIdx.y * GM_T, n0 = blockIdx.x * GM_T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wi = warp >> 1, wj = warp & 1;
-  double acc[2][4][2];
+  const int wi = warp >> 1, wj = warp & 1;          // 16 x 16 per warp
+  int kbeg = 0, kend = n;
+  if (a.a_tri == 1) kend = min(kend, m0 + GM_T);
+  if (a.a_tri == 2) kbeg = max(kbeg, m0);
+  if (a.b_tri == 1) kbeg = max(kbeg, n0);
+  if (a.b_tri == 2) kend = min(kend, n0 + GM_T);
+  double acc[2][2][2] = {};
+  // each thread moves 8 elements of each operand per k-tile; index order chosen so global reads coalesce
+  double ra[8], rb[8];
+  auto gload = [&](int k0) {
 #pragma unroll
-  for (int x = 0; x < 2; ++x)
-#pragma unroll
-    for (int y = 0; y < 4; ++y) { acc[x][y][0] = 0.0; acc[x][y][1] = 0.0; }
-  for (int k0 = 0; k0 < n; k0 += GM_K) {
-    for (int idx = tid; idx < GM_K * GM_T; idx += GM_THREADS) {
-      int kk, mm;
-      if (csA == 1) { mm = idx / GM_K; kk = idx - mm * GM_K; } else { kk = idx / GM_T; mm = idx - kk * GM_T; }
-      As[kk][mm] = (m0 + mm < n) ? A[(size_t)(m0 + mm) * rsA + (size_t)(k0 + kk) * csA] : 0.0;
-      int kb, nn;
-      if (rsB == 1) { nn = idx / GM_K; kb = idx - nn * GM_K; } else { kb = idx / GM_T; nn = idx - kb * GM_T; }
-      Bs[kb][nn] = (n0 + nn < n) ? B[(size_t)(k0 + kb) * rsB + (size_t)(n0 + nn) * csB] : 0.0;
+    for (int q = 0; q < 8; ++q) {
+      const int idx = tid + q * GM_THREADS;
+      int kk, mm, kb, nn;
+      if (a.csA == 1) { mm = idx >> 5; kk = idx & 31; } else { kk = idx >> 5; mm = idx & 31; }
+      if (a.rsB == 1) { nn = idx >> 5; kb = idx & 31; } else { kb = idx >> 5; nn = idx & 31; }
+      ra[q] = A[(size_t)(m0 + mm) * a.rsA + (size_t)(k0 + kk) * a.csA];
+      rb[q] = B[(size_t)(k0 + kb) * a.rsB + (size_t)(n0 + nn) * a.csB];
     }
-    __syncthreads();
+  };
+  auto sstore = [&](int buf) {
 #pragma unroll
-    for (int kk = 0; kk < GM_K; kk += 4) {
-      double af[2], bf[4];
-#pragma unroll
-      for (int x = 0; x < 2; ++x) af[x] = As[kk + t][16 * wi + 8 * x + g];
-#pragma unroll
-      for (int y = 0; y < 4; ++y) bf[y] = Bs[kk + t][32 * wj + 8 * y + g];
-#pragma unroll
-      for (int x = 0; x < 2; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+    for (int q = 0; q < 8; ++q) {
+      const int idx = tid + q * GM_THREADS;
+      int kk, mm, kb, nn;
+      if (a.csA == 1) { mm = idx >> 5; kk = idx & 31; } else { kk = idx >> 5; mm = idx & 31; }
+      if (a.rsB == 1) { nn = idx >> 5; kb = idx & 31; } else { kb = idx >> 5; nn = idx & 31; }
+      As[buf][kk][mm] = ra[q];
+      Bs[buf][kb][nn] = rb[q];
     }
+  };
+  if (kbeg < kend) {
+    gload(kbeg);
+    sstore(0);
     __syncthreads();
+    int buf = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += GM_K) {
+      const bool more = k0 + GM_K < kend;
+      if (more) gload(k0 + GM_K);
+#pragma unroll
+      for (int kk = 0; kk < GM_K; kk += 4) {
+        double af[2], bf[2];
+#pragma unroll
+        for (int x = 0; x < 2; ++x) af[x] = As[buf][kk + t][16 * wi + 8 * x + g];
+#pragma unroll
+        for (int y = 0; y < 2; ++y) bf[y] = Bs[buf][kk + t][16 * wj + 8 * y + g];
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+          for (int y = 0; y < 2; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+      }
+      if (more) sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
   }
 #pragma unroll
   for (int x = 0; x < 2; ++x)
 #pragma unroll
-    for (int y = 0; y < 4; ++y)
+    for (int y = 0; y < 2; ++y)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int i = m0 + 16 * wi + 8 * x + g, j = n0 + 32 * wj + 8 * y + 2 * t + e;
-        if (i < n && j < n) {
-          const size_t o = (size_t)i * n + j;
-          C[o] = alpha * acc[x][y][e] + (beta != 0.0 ? beta * C[o] : 0.0);
-        }
+        const int i = m0 + 16 * wi + 8 * x + g, j = n0 + 16 * wj + 8 * y + 2 * t + e;
+        const size_t o = (size_t)i * n + j;
+        const double v = a.alpha * acc[x][y][e] + (a.beta != 0.0 ? a.beta * C[o] : 0.0);
+        C[o] = v;
+        if (Ct) Ct[(size_t)j * n + i] = v;
       }
 }
 
-static int gemm(int n, const double* A, bool tA, const double* B, bool tB, double* C, double alpha, double beta,
-                cudaStream_t st) {
-  dim3 grid((n + GM_T - 1) / GM_T, (n + GM_T - 1) / GM_T);
-  MOBO_LAUNCH("gemm_kernel", st, gemm_kernel<<<grid, GM_THREADS, 0, st>>>(n, A, tA ? 1 : n, tA ? n : 1, B, tB ? 1 : n, tB ? n : 1, C, alpha, beta));
+struct GemmOperand { const double* p[MAX_BATCH]; bool trans; int tri; };
+
+static int gemm_batched(int nbatch, int n, const GemmOperand& A, const GemmOperand& B, double* const* C,
+                        double* const* Ct, double alpha, double beta, const double* const* skip_if_zero,
+                        cudaStream_t st) {
+  GemmArgs a;
+  a.n = n;
+  a.rsA = A.trans ? 1 : n; a.csA = A.trans ? n : 1;
+  a.rsB = B.trans ? 1 : n; a.csB = B.trans ? n : 1;
+  a.a_tri = A.tri; a.b_tri = B.tri;
+  a.alpha = alpha; a.beta = beta;
+  for (int i = 0; i < MAX_BATCH; ++i) {
+    a.p.A[i] = i < nbatch ? A.p[i] : nullptr;
+    a.p.B[i] = i < nbatch ? B.p[i] : nullptr;
+    a.p.C[i] = i < nbatch ? C[i] : nullptr;
+    a.p.Ct[i] = (i < nbatch && Ct) ? Ct[i] : nullptr;
+    a.skip_if_zero[i] = (i < nbatch && skip_if_zero) ? skip_if_zero[i] : nullptr;
+  }
+  dim3 grid(n / GM_T, n / GM_T, nbatch);
+  MOBO_LAUNCH("gemm_kernel", st, gemm_kernel<<<grid, GM_THREADS, 0, st>>>(a));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// elementwise helpers on MP x MP blocks
-// ---------------------------------------------------------------------------------------------------
-enum EwOp {
-  EW_TRANSPOSE = 0,      // out = in^T
-  EW_PAD_TRIL = 1,       // out(MP) = tril(in(M x M, ld M)) zero padded
-  EW_SUB = 2,            // out = in - in2
-  EW_SCALE = 3,          // out = s * in         (s read from device scalar * hs)
-  EW_TRIL_INPLACE = 4,   // out = tril(in)
-  EW_NEG_TRIL_DIAG = 5,  // out = -tril(in) + diag(s / L_ii)   (in2 = L)
-  EW_PHI = 6,            // out = tril(in) with halved diagonal
-  EW_SYM = 7,            // out = 1/2 (in + in^T)
-  EW_RANK1_ADD = 8,      // out += u v^T  (u = vec1, v = vec2)
-};
-__global__ void ew_kernel(int op, int M, int MP, const double* __restrict__ in, const double* __restrict__ in2,
-                          double* __restrict__ out, const double* __restrict__ sdev, double hs,
-                          const double* __restrict__ v1, const double* __restrict__ v2) {
+// LQ = tril(Lq) zero padded to MP
+__global__ void padtril_kernel(LayerBatch b) {
+  const int bi = blockIdx.y, M = b.M, MP = b.MP;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= MP * MP) return;
   const int i = idx / MP, j = idx - i * MP;
-  const double s = sdev ? sdev[0] * hs : hs;
-  switch (op) {
-    case EW_TRANSPOSE: out[idx] = in[(size_t)j * MP + i]; break;
-    case EW_PAD_TRIL: out[idx] = (i < M && j <= i) ? in[(size_t)i * M + j] : 0.0; break;
-    case EW_SUB: out[idx] = in[idx] - in2[idx]; break;
-    case EW_SCALE: out[idx] = s * in[idx]; break;
-    case EW_TRIL_INPLACE: out[idx] = j <= i ? in[idx] : 0.0; break;
-    case EW_NEG_TRIL_DIAG:
-      out[idx] = (j <= i ? -in[idx] : 0.0) + ((i == j && i < M) ? s / in2[idx] : 0.0);
-      break;
-    case EW_PHI: out[idx] = j < i ? in[idx] : (j == i ? 0.5 * in[idx] : 0.0); break;
-    case EW_SYM: out[idx] = 0.5 * (in[idx] + in[(size_t)j * MP + i]); break;
-    case EW_RANK1_ADD: out[idx] += v1[i] * v2[j]; break;
-  }
+  (b.ops[bi] + ops_block(MP, OPS_LQ))[idx] = (i < M && j <= i) ? b.Lq[bi][(size_t)i * M + j] : 0.0;
 }
 
-static int ew(int op, int M, int MP, const double* in, const double* in2, double* out, const double* sdev, double hs,
-              const double* v1, const double* v2, cudaStream_t st) {
-  MOBO_LAUNCH("ew_kernel", st, ew_kernel<<<(MP * MP + 255) / 256, 256, 0, st>>>(op, M, MP, in, in2, out, sdev, hs, v1, v2));
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
-}
-
-// beta = W m, alpha = W^T beta, KL pieces.  One CTA, warp-per-row GEMVs (coalesced over the row).
-__global__ void __launch_bounds__(256) finalize_kernel(int M, int MP, const double* __restrict__ m, double* ops) {
-  __shared__ double sb[MAX_MP_FINAL];
-  __shared__ double red[4][8];
+// beta = W m and the KL pieces; warp per row, the last CTA of each matrix folds the row statistics in row order.
+constexpr int FIN_WARPS = 8;
+struct FinBatch { double* rowstat[MAX_BATCH]; unsigned int* counter[MAX_BATCH]; };
+__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(LayerBatch b, FinBatch f) {
+  const int bi = blockIdx.y, M = b.M, MP = b.MP;
+  double* ops = b.ops[bi];
   const double* L = ops + ops_block(MP, OPS_L);
   const double* W = ops + ops_block(MP, OPS_W);
-  const double* WT = ops + ops_block(MP, OPS_WT);
   const double* H = ops + ops_block(MP, OPS_H);
   const double* LQ = ops + ops_block(MP, OPS_LQ);
+  const double* m = b.m[bi];
   double* beta = ops + ops_beta(MP);
-  double* alpha = ops + ops_alpha(MP);
-  double* scal = ops + ops_scal(MP);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = warp; i < MP; i += 8) {
-    double s = 0.0;
+  double* rowstat = f.rowstat[bi];       // [4][MP]: beta^2, |H_i|^2, 2 log L_ii, log Lq_ii^2
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * FIN_WARPS + warp;
+  if (i < MP) {
+    double s = 0.0, h = 0.0;
     if (i < M)
       for (int k = lane; k <= i; k += 32) s = fma(W[(size_t)i * MP + k], m[k], s);
+    for (int k = lane; k <= i; k += 32) { const double v = H[(size_t)i * MP + k]; h = fma(v, v, h); }
     s = warp_sum(s);
-    if (lane == 0) { sb[i] = s; beta[i] = s; }
-  }
-  __syncthreads();
-  for (int j = warp; j < MP; j += 8) {
-    double s = 0.0;
-    for (int i = j + lane; i < MP; i += 32) s = fma(WT[(size_t)j * MP + i], sb[i], s);
-    s = warp_sum(s);
-    if (lane == 0) alpha[j] = s;
-  }
-  double b2 = 0.0, ldp = 0.0, ldq = 0.0, h2 = 0.0;
-  for (int j = tid; j < MP; j += 256) {
-    b2 = fma(sb[j], sb[j], b2);
-    if (j < M) {
-      ldp += 2.0 * log(L[(size_t)j * MP + j]);
-      const double q = LQ[(size_t)j * MP + j];
-      ldq += log(q * q);
+    h = warp_sum(h);
+    if (lane == 0) {
+      beta[i] = s;
+      rowstat[i] = s * s;
+      rowstat[MP + i] = h;
+      const double q = i < M ? LQ[(size_t)i * MP + i] : 1.0;
+      rowstat[2 * MP + i] = i < M ? 2.0 * log(L[(size_t)i * MP + i]) : 0.0;
+      rowstat[3 * MP + i] = log(q * q);
     }
   }
-  for (int idx = tid; idx < MP * MP; idx += 256) h2 = fma(H[idx], H[idx], h2);
-  b2 = warp_sum(b2); ldp = warp_sum(ldp); ldq = warp_sum(ldq); h2 = warp_sum(h2);
-  if (lane == 0) { red[0][warp] = b2; red[1][warp] = ldp; red[2][warp] = ldq; red[3][warp] = h2; }
+  __shared__ bool last;
+  __threadfence();
   __syncthreads();
-  if (tid == 0) {
+  if (threadIdx.x == 0) last = atomicAdd(f.counter[bi], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && warp == 0) {
+    __threadfence();
     double v[4];
-    for (int q = 0; q < 4; ++q) { v[q] = 0.0; for (int w = 0; w < 8; ++w) v[q] += red[q][w]; }
-    scal[SC_BETA2] = v[0]; scal[SC_LOGDET_P] = v[1]; scal[SC_LOGDET_Q] = v[2]; scal[SC_H2] = v[3];
-    scal[SC_KL] = 0.5 * (v[1] - v[2] + v[0] + v[3] - (double)M);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double s = 0.0;
+      for (int r = lane; r < MP; r += 32) s += ((volatile double*)rowstat)[q * MP + r];
+      v[q] = warp_sum(s);
+    }
+    if (lane == 0) {
+      double* scal = ops + ops_scal(MP);
+      scal[SC_BETA2] = v[0]; scal[SC_H2] = v[1]; scal[SC_LOGDET_P] = v[2]; scal[SC_LOGDET_Q] = v[3];
+      scal[SC_KL] = 0.5 * (v[2] - v[3] + v[0] + v[1] - (double)M);
+      *f.counter[bi] = 0u;
+    }
   }
 }
 
-// dbeta = W dalpha + dkl beta ; dm = W^T dbeta.  One CTA.  Writes dbeta (MP) and dm (M).
-__global__ void __launch_bounds__(256) dbeta_kernel(int M, int MP, const double* __restrict__ ops,
-                                                   const double* __restrict__ dalpha, const double* __restrict__ dkl,
-                                                   double* __restrict__ dbeta_out, double* __restrict__ dm) {
-  __shared__ double sb[MAX_MP_FINAL];
-  const double* W = ops + ops_block(MP, OPS_W);
-  const double* WT = ops + ops_block(MP, OPS_WT);
-  const double* beta = ops + ops_beta(MP);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double gk = dkl[0];
-  for (int i = warp; i < MP; i += 8) {
-    double s = 0.0;
-    for (int k = lane; k <= i; k += 32) s = fma(W[(size_t)i * MP + k], dalpha[k], s);
-    s = warp_sum(s);
-    if (lane == 0) { s += gk * beta[i]; sb[i] = s; dbeta_out[i] = s; }
-  }
-  __syncthreads();
-  for (int j = warp; j < M; j += 8) {
-    double s = 0.0;
-    for (int i = j + lane; i < MP; i += 32) s = fma(WT[(size_t)j * MP + i], sb[i], s);
-    s = warp_sum(s);
-    if (lane == 0) dm[j] = s;
-  }
+// dm = W^T (b + g beta).  Warp per row of W^T.
+struct VecBatch {
+  const double* WT[MAX_BATCH]; const double* b[MAX_BATCH]; const double* beta[MAX_BATCH]; const double* dkl[MAX_BATCH];
+  double* dm[MAX_BATCH];
+};
+__global__ void __launch_bounds__(256) white_vec_kernel(VecBatch v, int M, int MP) {
+  const int bi = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= M) return;
+  const double* row = v.WT[bi] + (size_t)j * MP;
+  const double g = v.dkl[bi][0];
+  double s = 0.0;
+  for (int i = j + lane; i < MP; i += 32) s = fma(row[i], v.b[bi][i] + g * v.beta[bi][i], s);
+  s = warp_sum(s);
+  if (lane == 0) v.dm[bi][j] = s;
 }
 
-// dLq (M x M, ld M) = tril(X)[:M,:M] - dkl * diag(1 / Lq_ii)
-__global__ void dlq_extract_kernel(int M, int MP, const double* __restrict__ X, const double* __restrict__ LQ,
-                                   const double* __restrict__ dkl, double* __restrict__ dLq) {
+// whitened gradient core  N = A1 - V - V^T - 1/2 (beta b^T + b beta^T) + g/2 (I - beta beta^T - G2)  (dP = W^T N W)
+// and F = 2 A2 + g I  (dLq = tril(W^T F H) - g diag(1/Lq_ii));  A1 = A2 - Ac when some row was clamped.
+struct CombineBatch {
+  const double* A2[MAX_BATCH]; const double* Ac[MAX_BATCH]; const double* V[MAX_BATCH]; const double* G2[MAX_BATCH];
+  const double* b[MAX_BATCH]; const double* beta[MAX_BATCH]; const double* dkl[MAX_BATCH];
+  const double* clamp_flag[MAX_BATCH]; double* N[MAX_BATCH]; double* F[MAX_BATCH];
+};
+__global__ void combine_kernel(CombineBatch c, int MP) {
+  const int bi = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= MP * MP) return;
+  const int i = idx / MP, j = idx - i * MP;
+  const size_t tr = (size_t)j * MP + i;
+  const double g = c.dkl[bi][0];
+  const bool clamped = c.clamp_flag[bi] && *c.clamp_flag[bi] != 0.0;
+  const double a2 = 0.5 * (c.A2[bi][idx] + c.A2[bi][tr]);
+  const double a1 = clamped ? a2 - 0.5 * (c.Ac[bi][idx] + c.Ac[bi][tr]) : a2;
+  const double bi_ = c.b[bi][i], bj_ = c.b[bi][j], be_i = c.beta[bi][i], be_j = c.beta[bi][j];
+  const double eye = i == j ? 1.0 : 0.0;
+  c.N[bi][idx] = a1 - c.V[bi][idx] - c.V[bi][tr] - 0.5 * (be_i * bj_ + bi_ * be_j) +
+                 0.5 * g * (eye - be_i * be_j - c.G2[bi][idx]);
+  c.F[bi][idx] = 2.0 * a2 + g * eye;
+}
+
+// dLq (M x M, ld M) = tril(E)[:M,:M] - g diag(1 / Lq_ii)
+struct DlqBatch { const double* E[MAX_BATCH]; const double* LQ[MAX_BATCH]; const double* dkl[MAX_BATCH]; double* dLq[MAX_BATCH]; };
+__global__ void dlq_extract_kernel(DlqBatch q, int M, int MP) {
+  const int bi = blockIdx.y;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * M) return;
   const int i = idx / M, j = idx - i * M;
-  double v = j <= i ? X[(size_t)i * MP + j] : 0.0;
-  if (i == j) v -= dkl[0] / LQ[(size_t)i * MP + i];
-  dLq[idx] = v;
+  double v = j <= i ? q.E[bi][(size_t)i * MP + j] : 0.0;
+  if (i == j) v -= q.dkl[bi][0] / q.LQ[bi][(size_t)i * MP + i];
+  q.dLq[bi][idx] = v;
 }
 
 }  // namespace mobo

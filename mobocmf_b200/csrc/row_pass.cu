@@ -46,9 +46,8 @@ struct RowArgs {
   double* var;
   double* craw;            // optional: k_xx - |t|^2 before the clamp (mask for the backward)
   unsigned int* clamp_count; // optional: number of rows whose k_xx - |t|^2 was clamped
-  double* Ksave;           // optional [R][MP]
-  double* Tsave;           // optional fragment-major [tile][warp][32][32]
-  double* Usave;
+  double* Tsave;           // optional row-major [R][MP]: whitened rows t = W k
+  double* Usave;           // optional fragment-major [tile][warp][32][32]: u = H^T t
   // backward inputs / outputs
   const double* dmu;
   const double* dvar;
@@ -245,12 +244,6 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_fwd_kernel(const __grid_co
       Ks[(size_t)r * ldb + j] = (j < a.M && r < nvalid) ? kern_pair(sm, r, j) : 0.0;
     }
     __syncthreads();
-    if (a.Ksave) {
-      for (int idx = tid; idx < nvalid * MP; idx += ROW_THREADS) {
-        const int r = idx / MP, j = idx - r * MP;
-        a.Ksave[(size_t)(row0 + r) * MP + j] = Ks[(size_t)r * ldb + j];
-      }
-    }
     // ---- t = W k ----
     double acc[2][2][4][2];
     zero_acc(acc);
@@ -290,11 +283,16 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_fwd_kernel(const __grid_co
             sm.red[1][p][32 * half + 8 * ct + 2 * t + e] = m;
           }
         }
-      if (a.Tsave) save_acc_frag(acc, a.Tsave, tile, nact, wact, lane);
     }
     __syncthreads();   // every warp is done reading K
     if (active) store_acc_to_tile(acc, Ks, ldb, sA, sB, half, lane);
     __syncthreads();
+    if (a.Tsave) {     // whitened rows t = W k, row-major [R][MP], for the backward (SYRK statistics and dt)
+      for (int idx = tid; idx < nvalid * MP; idx += ROW_THREADS) {
+        const int r = idx / MP, j = idx - r * MP;
+        a.Tsave[(size_t)(row0 + r) * MP + j] = Ks[(size_t)r * ldb + j];
+      }
+    }
     // ---- u = H^T t ----
     if (active) {
       zero_acc(acc);
@@ -337,8 +335,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_fwd_kernel(const __grid_co
 // backward of the row pass: given d loss/d mu_r, d loss/d var_r
 //   dt = dmu beta - 2 dvar (mask t - H u);  dk = W^T dt
 //   then through the covariance function: d theta, d zf (inducing propagated column), d f_r, d x_r.
-// The pieces that only need K itself,  A2 = sum_r dvar_r k k^T  and  dalpha = sum_r dmu_r k  (alpha = W^T beta),
-// are accumulated by syrk_kernel from the saved K and consumed by the operator backward (matrix_ops.cu).
+// The whitened second-order statistics  A2 = sum_r dvar_r t t^T  and  b = sum_r dmu_r t  (t = W k)
+// are accumulated by syrk_kernel from the saved T and consumed by the operator backward (matrix_ops.cu).
 // ---------------------------------------------------------------------------------------------------
 template <bool PARAM, bool XGRAD>
 __global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_kernel(const __grid_constant__ RowArgs a) {
@@ -387,18 +385,26 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_kernel(const __grid_co
     if (active) {
       zero_acc(acc);
       slab_gemm<false>(acc, H, MP, Ks, ldb, sA, sB, half, lane);
-      const double* tp = a.Tsave + (((size_t)tile * nact + wact) * 32) * 32 + lane;
+    }
+    __syncthreads();   // u is no longer needed: stage the saved t tile through shared memory
+    for (int idx = tid; idx < TR * MP; idx += ROW_THREADS) {
+      const int r = idx / MP, j = idx - r * MP;
+      Ks[(size_t)r * ldb + j] = r < nvalid ? a.Tsave[(size_t)(row0 + r) * MP + j] : 0.0;
+    }
+    __syncthreads();
+    if (active) {
 #pragma unroll
       for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
         for (int ib = 0; ib < 2; ++ib) {
-          const double bi = __ldg(beta + 16 * (sl == 0 ? sA : sB) + 8 * ib + g);
+          const int i = 16 * (sl == 0 ? sA : sB) + 8 * ib + g;
+          const double bi = __ldg(beta + i);
 #pragma unroll
           for (int ct = 0; ct < 4; ++ct)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int r = 32 * half + 8 * ct + 2 * t + e;
-              const double tv = __ldg(tp + (size_t)(((sl * 2 + ib) * 4 + ct) * 2 + e) * 32);
+              const double tv = Ks[(size_t)r * ldb + i];
               acc[sl][ib][ct][e] = sm.dmu[r] * bi - 2.0 * sm.dvar[r] * (sm.mask[r] * tv - acc[sl][ib][ct][e]);
             }
         }
@@ -575,7 +581,7 @@ __global__ void reduce_partials_kernel(const double* __restrict__ part, int nblo
 }
 
 // ---------------------------------------------------------------------------------------------------
-// A2 = sum_r w_r k_r k_r^T (lower 64x64 tiles) from the saved K [R][MP]; split over row chunks, partial
+// A2 = sum_r w_r t_r t_r^T (lower 64x64 tiles) from the saved whitened rows T [R][MP]; split over row chunks, partial
 // tiles reduced in a fixed order by syrk_reduce_kernel which also mirrors to the full symmetric matrix.
 // w_r = dvar_r (which = 0) or dvar_r * [clamped row] (which = 1, only when some row was clamped).
 // ---------------------------------------------------------------------------------------------------
@@ -657,8 +663,10 @@ __global__ void __launch_bounds__(SY_THREADS) syrk_kernel(const double* __restri
 }
 
 __global__ void syrk_reduce_kernel(const double* __restrict__ part, int ntiles, int nchunk, int MP,
-                                   double* __restrict__ A, int which, const unsigned int* __restrict__ clamp_count) {
+                                   double* __restrict__ A, int which, const unsigned int* __restrict__ clamp_count,
+                                   double* __restrict__ clamp_flag_out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0 && which == 1 && clamp_flag_out) *clamp_flag_out = clamp_count ? (double)(*clamp_count) : 0.0;
   if (idx >= MP * MP) return;
   if (which == 1 && (clamp_count == nullptr || *clamp_count == 0u)) { A[idx] = 0.0; return; }
   int i = idx / MP, j = idx - (idx / MP) * MP;
@@ -750,12 +758,12 @@ size_t syrk_part_doubles(int MP, long long R) { return (size_t)syrk_ntiles(MP) *
 // part: syrk_part_doubles(MP, R) doubles of scratch; part_alpha: nchunk * MP doubles (which == 0 only)
 int launch_syrk(const double* K, const double* dvar, const double* craw, int which, int MP, long long R,
                 double* part, double* A, const unsigned int* clamp_count, const double* dmu, double* part_alpha,
-                double* dalpha, cudaStream_t st) {
+                double* dalpha, double* clamp_flag_out, cudaStream_t st) {
   const int nt = syrk_ntiles(MP), nc = syrk_nchunk(MP, R);
   dim3 grid(nt, nc);
   MOBO_LAUNCH("syrk_kernel", st, syrk_kernel<<<grid, SY_THREADS, 0, st>>>(K, dvar, craw, which, MP, R, nc, part, clamp_count, dmu,
                                            which == 0 ? part_alpha : nullptr));
-  MOBO_LAUNCH("syrk_reduce_kernel", st, syrk_reduce_kernel<<<(MP * MP + 255) / 256, 256, 0, st>>>(part, nt, nc, MP, A, which, clamp_count));
+  MOBO_LAUNCH("syrk_reduce_kernel", st, syrk_reduce_kernel<<<(MP * MP + 255) / 256, 256, 0, st>>>(part, nt, nc, MP, A, which, clamp_count, clamp_flag_out));
   if (which == 0 && part_alpha && dalpha)
     MOBO_LAUNCH("reduce_partials_kernel", st, reduce_partials_kernel<<<(MP + 127) / 128, 128, 0, st>>>(part_alpha, nc, MP, MP, dalpha, 0));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;

@@ -24,7 +24,7 @@ def ops_layout(M):
     MP = padded_m(M)
     MP2 = MP * MP
     return {"MP": MP, "L": 0, "W": MP2, "WT": 2 * MP2, "H": 3 * MP2, "HT": 4 * MP2, "P": 5 * MP2, "LQ": 6 * MP2,
-            "beta": 7 * MP2, "alpha": 7 * MP2 + MP, "scal": 7 * MP2 + 2 * MP, "size": 7 * MP2 + 2 * MP + 16}
+            "beta": 7 * MP2, "alpha": 7 * MP2 + MP, "scal": 7 * MP2 + 2 * MP, "size": 7 * MP2 + 6 * MP + 16}
 
 
 def _c(t):
@@ -88,28 +88,26 @@ class _LayerRows(torch.autograd.Function):
         need_bwd = any(ctx.needs_input_grad)
         craw = torch.empty(R, dtype=torch.float64, device=dev) if (need_bwd and training) else None
         cnt = torch.zeros(1, dtype=torch.int32, device=dev) if (need_bwd and training) else None
-        Ks = Ts = Us = None
+        Ts = Us = None
         if need_bwd:
             nsave = lib.mobo_rows_save_doubles(M, R)
-            Ks = torch.empty(nsave, dtype=torch.float64, device=dev)
             Ts = torch.empty(nsave, dtype=torch.float64, device=dev)
             Us = torch.empty(nsave, dtype=torch.float64, device=dev)
         _lib.check(lib.mobo_layer_rows_fwd(kind, d, M, _lib.ptr(Zx_), _lib.ptr(zf_), _lib.ptr(theta_),
                                            _lib.ptr(ops_), _lib.ptr(x_), xrep, _lib.ptr(mu_prev_),
                                            _lib.ptr(var_prev_), prep, _lib.ptr(eps_), eps_mod, _lib.ptr(f_direct_),
                                            R, int(training), _lib.ptr(mu), _lib.ptr(var), _lib.ptr(craw),
-                                           _lib.ptr(cnt), _lib.ptr(Ks), _lib.ptr(Ts), _lib.ptr(Us),
+                                           _lib.ptr(cnt), _lib.ptr(Ts), _lib.ptr(Us),
                                            _lib.stream_ptr()), "mobo_layer_rows_fwd")
         if need_bwd:
-            ctx.save_for_backward(ops_, theta_, zf_, Zx_, x_, mu_prev_, var_prev_, eps_, f_direct_, craw, cnt, Ks,
-                                  Ts, Us)
+            ctx.save_for_backward(ops_, theta_, zf_, Zx_, x_, mu_prev_, var_prev_, eps_, f_direct_, craw, cnt, Ts, Us)
             ctx.cfg = (kind, xrep, prep, eps_mod, R, int(training))
         return mu, var
 
     @staticmethod
     def backward(ctx, dmu, dvar):
         lib = _lib.load()
-        ops, theta, zf, Zx, x, mu_prev, var_prev, eps, f_direct, craw, cnt, Ks, Ts, Us = ctx.saved_tensors
+        ops, theta, zf, Zx, x, mu_prev, var_prev, eps, f_direct, craw, cnt, Ts, Us = ctx.saved_tensors
         kind, xrep, prep, eps_mod, R, training = ctx.cfg
         M, d = Zx.shape
         dev = Zx.device
@@ -127,7 +125,7 @@ class _LayerRows(torch.autograd.Function):
         _lib.check(lib.mobo_layer_rows_bwd(kind, d, M, _lib.ptr(Zx), _lib.ptr(zf), _lib.ptr(theta), _lib.ptr(ops),
                                            _lib.ptr(x), xrep, _lib.ptr(mu_prev), _lib.ptr(var_prev), prep,
                                            _lib.ptr(eps), eps_mod, _lib.ptr(f_direct), R, training, _lib.ptr(dmu),
-                                           _lib.ptr(dvar), _lib.ptr(craw), _lib.ptr(cnt), _lib.ptr(Ks),
+                                           _lib.ptr(dvar), _lib.ptr(craw), _lib.ptr(cnt),
                                            _lib.ptr(Ts), _lib.ptr(Us), int(want_param), _lib.ptr(df),
                                            _lib.ptr(dxrow), _lib.ptr(dtheta), _lib.ptr(dzf), _lib.ptr(gops),
                                            _lib.ptr(work), _lib.stream_ptr()), "mobo_layer_rows_bwd")
