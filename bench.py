@@ -107,30 +107,47 @@ def run_ours(args):
     elbo = VariationalELBOMF(model, cfg["N"], cfg["L"])
     model.fix_variational_hypers(False)
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.Adam([{"params": params}], lr=0.001)
     xd, yd, fd = x.to(dev), y.to(dev), fid.to(dev)
     B, S, N = cfg["B"], cfg["S"], cfg["N"]
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     # pinned host staging for the end-to-end arm
     xh, yh, fh = x.pin_memory(), y.pin_memory(), fid.pin_memory()
 
-    def one_step(xb, yb, fb):
-        opt.zero_grad(set_to_none=True)
-        with settings.num_likelihood_samples(1):
-            out = model(xb, num_samples=S)
-            res = elbo(out, yb.T, fb)
-        loss = -res[0]
-        loss.backward()
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            off = 0
-            for p in params:
-                n = p.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
-        opt.step()
-        return loss
+    if args.path == "fused":
+        # the product path of the fitter's hot loop: mobo_elbo_step (one enqueue, no autograd) + mobo_adam
+        from mobocmf_b200.fused import Adam, FusedELBOStep
+        from mobocmf_b200.util.distributed import broadcast_parameters
+        broadcast_parameters(model)
+        fstep = FusedELBOStep(model, elbo)
+        opt = Adam([{"params": params}], lr=0.001)
+
+        def one_step(xb, yb, fb):
+            loss, _ = fstep(xb, yb, fb, num_samples=S)
+            if world > 1:
+                fstep.flat.all_reduce()          # ONE all-reduce of the flat gradient buffer (NCCL over NVLink)
+            opt.step()
+            return loss
+    else:
+        # composable path: the same kernels under torch autograd + torch.optim.Adam (kept for comparison)
+        opt = torch.optim.Adam([{"params": params}], lr=0.001)
+
+        def one_step(xb, yb, fb):
+            opt.zero_grad(set_to_none=True)
+            with settings.num_likelihood_samples(1):
+                out = model(xb, num_samples=S)
+                res = elbo(out, yb.T, fb)
+            loss = -res[0]
+            loss.backward()
+            if world > 1:
+                flat = torch.cat([p.grad.reshape(-1) for p in params])
+                dist.all_reduce(flat)
+                off = 0
+                for p in params:
+                    n = p.numel()
+                    p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                    off += n
+            opt.step()
+            return loss
 
     def device_step():
         idx = torch.randint(0, N, (B,), device=dev, generator=g)
@@ -145,7 +162,7 @@ def run_ours(args):
         torch.index_select(xh, 0, idx, out=hb[0]); torch.index_select(yh, 0, idx, out=hb[1])
         torch.index_select(fh, 0, idx, out=hb[2])
         xb, yb, fb = (t.to(dev, non_blocking=True) for t in hb)
-        return float(one_step(xb, yb, fb))       # device -> host read of the step's loss
+        return float(one_step(xb, yb, fb).detach())       # device -> host read of the step's loss
 
     def barrier():
         if world > 1:
@@ -327,6 +344,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--path", default="fused", choices=["fused", "composable"],
+                    help="fused: mobo_elbo_step + mobo_adam (product hot loop); composable: autograd over the same kernels")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-acq", action="store_true", help="skip the acquisition slice")
     args = ap.parse_args()

@@ -102,6 +102,69 @@ int mobo_layer_rows_bwd(int kind, int d, int M, const double* Zx, const double* 
 int mobo_kzz(int kind, int d, int M, const double* Zx, const double* zf, const double* theta, double jitter,
              double* P, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused ELBO step: the body of BlackBoxMFDGPFitter._update_model up to the gradients
+ * (mobocmf/util/blackbox_mfdgp_fitter.py:161-168: model(x), elbo(output, y.T, fid), loss = -elbo, loss.backward())
+ * as ONE enqueue of kernels without host synchronisation (CUDA-graph capturable):
+ * constraint transforms (softplus / Interval sigmoid, mobocmf/models/mfdgp.py:116), operator chain of every layer,
+ * the L fused row passes (MFDGP.forward, mobocmf/models/mfdgp.py:174-196), the ELBO
+ * (VariationalELBOMF.forward, mobocmf/mlls/variational_elbo_mf.py:24-51), the complete backward and the assembly of
+ * d loss / d RAW parameter.  Preconditions (the host mirror checks them and otherwise uses the composable entry
+ * points above): every layer shares the inducing inputs Zx (quirk Q4, so Z_l = [Zx, m_{l-1}]), training mode.
+ * S > 1 (not in the reference): layer 0 on B rows, layers >= 1 on B*S rows (row b*S+s), data terms
+ * averaged over s.  All pointers are device pointers.
+ * ------------------------------------------------------------------------------------------------------------ */
+#define MOBO_MAX_LAYERS 8
+#define MOBO_MAX_THETA 21            /* 5 + 2 * 8 */
+
+typedef struct mobo_layer_desc {
+  const double* Zx;                            /* M x d shared inducing inputs                                  */
+  const double* raw_theta[MOBO_MAX_THETA];     /* address of each RAW kernel hyper-parameter, in theta order     */
+  double* g_raw_theta[MOBO_MAX_THETA];         /* where d loss / d raw goes; NULL = frozen                       */
+  const double* m;                             /* variational_mean [M]                                           */
+  const double* Lq;                            /* chol_variational_covar [M x M] (tril applied inside)           */
+  double* g_m;                                 /* NULL = frozen                                                  */
+  double* g_Lq;                                /* NULL = frozen; receives the lower triangle, zeros above        */
+  const double* raw_noise;                     /* likelihood raw_noise [1]                                       */
+  double* g_raw_noise;                         /* NULL = frozen                                                  */
+  double noise_lower, noise_upper;             /* Interval bounds (mobocmf/models/mfdgp.py:116)                  */
+  const double* eps;                           /* layer >= 1: B*S standard normals (layers/...py:274); layer 0: NULL */
+} mobo_layer_desc;
+
+typedef struct mobo_step_desc {
+  int L, d, M, S;
+  long long B, num_data;
+  double jitter;
+  const double* x;                             /* B x d                                                          */
+  const double* y;                             /* B                                                              */
+  const double* fid;                           /* B, fidelity index stored as double (as the reference does)     */
+  mobo_layer_desc layer[MOBO_MAX_LAYERS];
+  double* out;                                 /* [0] loss = -ELBO, [1] KL*B/N, [2] data term, [3] status: 0 ok,
+                                                  l+1 = Cholesky of layer l failed (NotPSDError upstream)        */
+  double* workspace;                           /* mobo_elbo_step_workspace_doubles(...) doubles                  */
+  int accumulate;                              /* 0: gradients are overwritten, 1: added to                      */
+} mobo_step_desc;
+
+size_t mobo_elbo_step_workspace_doubles(int L, int d, int M, int S, long long B);
+int mobo_elbo_step(const mobo_step_desc* desc, void* stream);
+
+/* torch.optim.Adam update (mobocmf/util/blackbox_mfdgp_fitter.py:126,132,259; defaults betas (0.9, 0.999),
+ * eps 1e-8, no weight decay) of nt <= 64 tensors in one launch.  step = 1-based step count after increment. */
+typedef struct mobo_adam_tensor { double* p; const double* g; double* exp_avg; double* exp_avg_sq; long long n; } mobo_adam_tensor;
+int mobo_adam(int nt, const mobo_adam_tensor* tensors, double lr, double beta1, double beta2, double eps,
+              long long step, void* stream);
+
+/* Acquisition chain of ONE MFDGP in eval mode: MFDGP.predict_for_acquisition (mobocmf/models/mfdgp.py:237-262) for n
+ * candidates x S fixed normals per layer, up to layer `fidelity`, from precomputed operator buffers (the parameters
+ * are constants during optimize_acqf).  theta[l]: CONSTRAINED hyper-parameters; samples[l]: S normals of layer l >= 1
+ * (layers/...py:161); zf[l]: m_{l-1}.  Outputs out_mu[n], out_var[n].  scratch: 4 * n * S doubles. */
+int mobo_acq_moments(int fidelity, int d, int M, int S, long long n, const double* Zx, const double* const* zf,
+                     const double* const* theta, const double* const* ops, const double* const* samples,
+                     const double* raw_noise, double noise_lower, double noise_upper, const double* X,
+                     double* out_mu, double* out_var, double* scratch, void* stream);
+/* out[i] (+)= 1/2 max(0, log vu[i] - log vc[i])   (_JES_MFDGP.forward, acquisition_functions/JESMOC_MFDGP.py:52) */
+int mobo_jes(const double* var_uncond, const double* var_cond, long long n, int accumulate, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,14 @@ class _JES_MFDGP(torch.nn.Module):
         with settings.num_likelihood_samples(1):
             _, pred_variances_cond = self.mfdgp_cond.predict_for_acquisition(X, self.fidelity)
         self.mfdgp_cond.train()
+        if not (pred_variances_uncond.requires_grad or pred_variances_cond.requires_grad) and \
+                pred_variances_uncond.is_cuda:
+            from .. import _lib
+            out = torch.empty_like(pred_variances_uncond)
+            _lib.check(_lib.load().mobo_jes(_lib.ptr(pred_variances_uncond.contiguous()),
+                                            _lib.ptr(pred_variances_cond.contiguous()), out.numel(), 0,
+                                            _lib.ptr(out), _lib.stream_ptr()), "mobo_jes")
+            return out
         return 0.5 * torch.clamp(torch.log(pred_variances_uncond) - torch.log(pred_variances_cond), min=0.0)
 
 

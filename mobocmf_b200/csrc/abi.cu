@@ -4,6 +4,7 @@
 #include "../../include/mobocmf_b200.h"
 #include "matrix_ops.cu"
 #include "row_pass.cu"
+#include "step.cu"
 
 using namespace mobo;
 
@@ -85,7 +86,7 @@ int mobo_kzz(int kind, int d, int M, const double* Zx, const double* zf, const d
   double* fake_ops = P - ops_block(MP, OPS_P);
   MOBO_TRY(fill_batch(b, 1, &kind, d, M, &Zx, &zf, &theta, nullptr, nullptr, &fake_ops));
   cudaStream_t st = (cudaStream_t)stream;
-  MOBO_LAUNCH("kzz_kernel", st, kzz_kernel<<<dim3((MP * MP + 255) / 256, 1), 256, 0, st>>>(b, jitter, OPS_P));
+  MOBO_LAUNCH("kzz_kernel", st, kzz_kernel<<<dim3((MP * MP + 255) / 256, 1), 256, 0, st>>>(b, jitter, OPS_P, 0));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -102,7 +103,7 @@ int mobo_model_precompute(int nl, const int* kinds, int d, int M, const double* 
     attr_done = true;
   }
   const dim3 ew_grid((MP * MP + 255) / 256, nl);
-  MOBO_LAUNCH("kzz_kernel", st, kzz_kernel<<<ew_grid, 256, 0, st>>>(b, jitter, OPS_P));
+  MOBO_LAUNCH("kzz_kernel", st, kzz_kernel<<<ew_grid, 256, 0, st>>>(b, jitter, OPS_P, 1));
   const size_t chol_smem = (size_t)(64 * CH_LD + (size_t)MP * CH_LD) * sizeof(double);
   MOBO_LAUNCH("chol_inv_kernel", st, chol_inv_kernel<<<nl, CH_THREADS, chol_smem, st>>>(b));
   MOBO_LAUNCH("padtril_kernel", st, padtril_kernel<<<ew_grid, 256, 0, st>>>(b));
@@ -305,6 +306,229 @@ int mobo_layer_rows_bwd(int kind, int d, int M, const double* Zx, const double* 
                          training ? clamp_count : nullptr, nullptr, nullptr, nullptr,
                          gops + ops_scal(MP) + SC_CLAMP, st));
   }
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused ELBO step
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct StepLayout {
+  size_t theta[ST_MAX_LAYERS], ops[ST_MAX_LAYERS], gops[ST_MAX_LAYERS], mu[ST_MAX_LAYERS], var[ST_MAX_LAYERS],
+      craw[ST_MAX_LAYERS], dmu[ST_MAX_LAYERS], dvar[ST_MAX_LAYERS], df[ST_MAX_LAYERS], Ts[ST_MAX_LAYERS],
+      Us[ST_MAX_LAYERS], dtheta_rows[ST_MAX_LAYERS], dtheta_pre[ST_MAX_LAYERS], dzf_rows[ST_MAX_LAYERS],
+      dzf_pre[ST_MAX_LAYERS], dm_pre[ST_MAX_LAYERS], dLq_tmp[ST_MAX_LAYERS], pre_work[ST_MAX_LAYERS],
+      ell_part[ST_MAX_LAYERS];
+  long long R[ST_MAX_LAYERS];
+  int ell_blocks[ST_MAX_LAYERS];
+  size_t noise, clamp, rows_work, total;
+};
+
+StepLayout step_layout(int L, int d, int M, int S, long long B) {
+  StepLayout y;
+  size_t off = 0;
+  auto take = [&](size_t n) { const size_t o = off; off += (n + 15) / 16 * 16; return o; };
+  const int MP = padded(M);
+  y.noise = take(ST_MAX_LAYERS);
+  y.clamp = take(ST_MAX_LAYERS);
+  size_t rows_work = 0;
+  for (int l = 0; l < L; ++l) {
+    const long long R = l == 0 ? B : B * (long long)S;
+    y.R[l] = R;
+    y.ell_blocks[l] = (int)((R + ELL_THREADS - 1) / ELL_THREADS);
+    y.theta[l] = take(ST_MAX_THETA);
+    y.ops[l] = take(ops_size(MP));
+    y.gops[l] = take(ops_size(MP));
+    y.mu[l] = take(R); y.var[l] = take(R); y.craw[l] = take(R);
+    y.dmu[l] = take(R); y.dvar[l] = take(R); y.df[l] = take(R);
+    y.Ts[l] = take(mobo_rows_save_doubles(M, R));
+    y.Us[l] = take(mobo_rows_save_doubles(M, R));
+    y.dtheta_rows[l] = take(ST_MAX_THETA); y.dtheta_pre[l] = take(ST_MAX_THETA);
+    y.dzf_rows[l] = take(MP); y.dzf_pre[l] = take(MP); y.dm_pre[l] = take(MP);
+    y.dLq_tmp[l] = take((size_t)M * M);
+    y.pre_work[l] = take(mobo_precompute_bwd_work_doubles(M));
+    y.ell_part[l] = take(2 * (size_t)y.ell_blocks[l]);
+    const size_t w = mobo_rows_bwd_work_doubles(M, R);
+    rows_work = w > rows_work ? w : rows_work;
+  }
+  y.rows_work = take(rows_work);
+  y.total = off;
+  (void)d;
+  return y;
+}
+
+}  // namespace
+
+size_t mobo_elbo_step_workspace_doubles(int L, int d, int M, int S, long long B) {
+  if (L < 1 || L > ST_MAX_LAYERS) return 0;
+  return step_layout(L, d, M, S, B).total;
+}
+
+int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int L = D->L, d = D->d, M = D->M, S = D->S < 1 ? 1 : D->S;
+  if (L < 1 || L > ST_MAX_LAYERS || d > kMaxD || padded(M) > MAX_MP || D->B < 1) return -2;
+  const int MP = padded(M);
+  const StepLayout y = step_layout(L, d, M, S, D->B);
+  double* ws = D->workspace;
+  const double kl_scale = (double)D->B / (double)D->num_data;
+  unsigned int* clamp = reinterpret_cast<unsigned int*>(ws + y.clamp);
+
+  int kinds[ST_MAX_LAYERS];
+  const double* Zx[ST_MAX_LAYERS]; const double* zf[ST_MAX_LAYERS]; const double* theta[ST_MAX_LAYERS];
+  const double* m[ST_MAX_LAYERS]; const double* Lq[ST_MAX_LAYERS];
+  double* ops[ST_MAX_LAYERS]; const double* cops[ST_MAX_LAYERS]; const double* gops[ST_MAX_LAYERS];
+  double* pre_work[ST_MAX_LAYERS]; double* dtheta_pre[ST_MAX_LAYERS]; double* dzf_pre[ST_MAX_LAYERS];
+  double* dm_pre[ST_MAX_LAYERS]; double* dLq[ST_MAX_LAYERS];
+  for (int l = 0; l < L; ++l) {
+    const mobo_layer_desc& ld = D->layer[l];
+    kinds[l] = l == 0 ? 0 : 1;
+    Zx[l] = ld.Zx; zf[l] = l == 0 ? nullptr : D->layer[l - 1].m; theta[l] = ws + y.theta[l];
+    m[l] = ld.m; Lq[l] = ld.Lq;
+    ops[l] = ws + y.ops[l]; cops[l] = ops[l]; gops[l] = ws + y.gops[l];
+    pre_work[l] = ws + y.pre_work[l]; dtheta_pre[l] = ws + y.dtheta_pre[l]; dzf_pre[l] = ws + y.dzf_pre[l];
+    dm_pre[l] = ws + y.dm_pre[l];
+    dLq[l] = (ld.g_Lq && !D->accumulate) ? ld.g_Lq : ws + y.dLq_tmp[l];
+  }
+  // 1. raw -> constrained
+  {
+    PrepArgs a;
+    a.L = L; a.d = d; a.noise = ws + y.noise; a.clamp_count = clamp; a.dkl = kl_scale;
+    for (int l = 0; l < ST_MAX_LAYERS; ++l) {
+      const bool ok = l < L;
+      for (int i = 0; i < ST_MAX_THETA; ++i) a.raw_theta[l][i] = ok ? D->layer[l].raw_theta[i] : nullptr;
+      a.raw_noise[l] = ok ? D->layer[l].raw_noise : nullptr;
+      a.noise_lo[l] = ok ? D->layer[l].noise_lower : 0.0; a.noise_hi[l] = ok ? D->layer[l].noise_upper : 0.0;
+      a.theta[l] = ok ? ws + y.theta[l] : nullptr;
+      a.gops_scal[l] = ok ? ws + y.gops[l] + ops_scal(MP) : nullptr;
+      a.ops_scal[l] = ok ? ws + y.ops[l] + ops_scal(MP) : nullptr;
+    }
+    MOBO_LAUNCH("step_prep_kernel", st, step_prep_kernel<<<L, 96, 0, st>>>(a));
+  }
+  // 2. operator chain of every layer
+  MOBO_TRY(mobo_model_precompute(L, kinds, d, M, Zx, zf, theta, m, Lq, D->jitter, ops, stream));
+  // 3. forward row passes, low -> high fidelity
+  for (int l = 0; l < L; ++l) {
+    const long long R = y.R[l];
+    MOBO_TRY(mobo_layer_rows_fwd(kinds[l], d, M, Zx[l], zf[l], theta[l], ops[l], D->x, l == 0 ? 1 : S,
+                                 l == 0 ? nullptr : ws + y.mu[l - 1], l == 0 ? nullptr : ws + y.var[l - 1],
+                                 l == 0 ? 1 : (int)(R / y.R[l - 1]), D->layer[l].eps, R, nullptr, R, 1,
+                                 ws + y.mu[l], ws + y.var[l], ws + y.craw[l], clamp + l, ws + y.Ts[l], ws + y.Us[l],
+                                 stream));
+  }
+  // 4. ELBO terms and backward row passes, high -> low fidelity
+  for (int l = L - 1; l >= 0; --l) {
+    const long long R = y.R[l];
+    EllArgs e;
+    e.layer = l; e.R = R; e.S = l == 0 ? 1 : S; e.y = D->y; e.fid = D->fid;
+    e.mu = ws + y.mu[l]; e.var = ws + y.var[l]; e.noise = ws + y.noise;
+    e.df_next = l + 1 < L ? ws + y.df[l + 1] : nullptr;
+    e.eps_next = l + 1 < L ? D->layer[l + 1].eps : nullptr;
+    e.prep_next = l + 1 < L ? (int)(y.R[l + 1] / R) : 1;
+    e.dmu = ws + y.dmu[l]; e.dvar = ws + y.dvar[l]; e.part = ws + y.ell_part[l];
+    MOBO_LAUNCH("ell_kernel", st, ell_kernel<<<y.ell_blocks[l], ELL_THREADS, 0, st>>>(e));
+    MOBO_TRY(mobo_layer_rows_bwd(kinds[l], d, M, Zx[l], zf[l], theta[l], ops[l], D->x, l == 0 ? 1 : S,
+                                 l == 0 ? nullptr : ws + y.mu[l - 1], l == 0 ? nullptr : ws + y.var[l - 1],
+                                 l == 0 ? 1 : (int)(R / y.R[l - 1]), D->layer[l].eps, R, nullptr, R, 1,
+                                 ws + y.dmu[l], ws + y.dvar[l], ws + y.craw[l], clamp + l, ws + y.Ts[l],
+                                 ws + y.Us[l], 1, ws + y.df[l], nullptr, ws + y.dtheta_rows[l],
+                                 l == 0 ? nullptr : ws + y.dzf_rows[l], ws + y.gops[l], ws + y.rows_work, stream));
+  }
+  // 5. backward of the operator chains
+  MOBO_TRY(mobo_model_precompute_bwd(L, kinds, d, M, Zx, zf, theta, m, Lq, cops, gops, pre_work, dtheta_pre, dzf_pre,
+                                     dm_pre, dLq, stream));
+  // 6. gradient assembly
+  {
+    FinishArgs a;
+    a.L = L; a.d = d; a.M = M; a.MP = MP; a.kl_scale = kl_scale; a.out = D->out; a.accumulate = D->accumulate;
+    for (int l = 0; l < ST_MAX_LAYERS; ++l) {
+      const bool ok = l < L;
+      for (int i = 0; i < ST_MAX_THETA; ++i) {
+        a.raw_theta[l][i] = ok ? D->layer[l].raw_theta[i] : nullptr;
+        a.g_raw_theta[l][i] = ok ? D->layer[l].g_raw_theta[i] : nullptr;
+      }
+      a.dtheta_rows[l] = ok ? ws + y.dtheta_rows[l] : nullptr;
+      a.dtheta_pre[l] = ok ? ws + y.dtheta_pre[l] : nullptr;
+      a.dzf_rows[l] = (ok && l > 0) ? ws + y.dzf_rows[l] : nullptr;
+      a.dzf_pre[l] = (ok && l > 0) ? ws + y.dzf_pre[l] : nullptr;
+      a.dm_pre[l] = ok ? ws + y.dm_pre[l] : nullptr;
+      a.g_m[l] = ok ? D->layer[l].g_m : nullptr;
+      a.raw_noise[l] = ok ? D->layer[l].raw_noise : nullptr;
+      a.noise_lo[l] = ok ? D->layer[l].noise_lower : 0.0; a.noise_hi[l] = ok ? D->layer[l].noise_upper : 0.0;
+      a.g_raw_noise[l] = ok ? D->layer[l].g_raw_noise : nullptr;
+      a.ell_part[l] = ok ? ws + y.ell_part[l] : nullptr;
+      a.ell_blocks[l] = ok ? y.ell_blocks[l] : 0;
+      a.ops_scal[l] = ok ? ws + y.ops[l] + ops_scal(MP) : nullptr;
+    }
+    MOBO_LAUNCH("step_finish_kernel", st, step_finish_kernel<<<1, 256, 0, st>>>(a));
+  }
+  if (D->accumulate)
+    for (int l = 0; l < L; ++l)
+      if (D->layer[l].g_Lq) {
+        const long long n = (long long)M * M;
+        MOBO_LAUNCH("add_matrix_kernel", st,
+                    add_matrix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D->layer[l].g_Lq, dLq[l], n));
+      }
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int mobo_adam(int nt, const mobo_adam_tensor* tensors, double lr, double beta1, double beta2, double eps,
+              long long step, void* stream) {
+  if (nt < 1 || nt > ADAM_MAX_TENSORS || step < 1) return -2;
+  cudaStream_t st = (cudaStream_t)stream;
+  AdamArgs a;
+  a.nt = nt; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+  a.bc1 = 1.0 - pow(beta1, (double)step);
+  a.bc2_sqrt = sqrt(1.0 - pow(beta2, (double)step));
+  long long mx = 1;
+  for (int i = 0; i < ADAM_MAX_TENSORS; ++i) {
+    const bool ok = i < nt;
+    a.p[i] = ok ? tensors[i].p : nullptr; a.g[i] = ok ? tensors[i].g : nullptr;
+    a.m[i] = ok ? tensors[i].exp_avg : nullptr; a.v[i] = ok ? tensors[i].exp_avg_sq : nullptr;
+    a.n[i] = ok ? tensors[i].n : 0;
+    if (ok && tensors[i].n > mx) mx = tensors[i].n;
+  }
+  long long gx = (mx + 255) / 256;
+  if (gx > 64) gx = 64;
+  MOBO_LAUNCH("adam_kernel", st, adam_kernel<<<dim3((unsigned)gx, nt), 256, 0, st>>>(a));
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int mobo_acq_moments(int fidelity, int d, int M, int S, long long n, const double* Zx, const double* const* zf,
+                     const double* const* theta, const double* const* ops, const double* const* samples,
+                     const double* raw_noise, double noise_lower, double noise_upper, const double* X,
+                     double* out_mu, double* out_var, double* scratch, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fidelity < 0 || fidelity >= ST_MAX_LAYERS || n < 1 || S < 1) return -2;
+  const long long RS = n * (long long)S;
+  double* mu[2] = {scratch, scratch + 2 * RS};
+  double* var[2] = {scratch + RS, scratch + 3 * RS};
+  long long Rprev = n;
+  for (int l = 0; l <= fidelity; ++l) {
+    const long long R = l == 0 ? n : RS;
+    const int cur = l & 1, prv = cur ^ 1;
+    MOBO_TRY(mobo_layer_rows_fwd(l == 0 ? 0 : 1, d, M, Zx, l == 0 ? nullptr : zf[l], theta[l], ops[l], X,
+                                 l == 0 ? 1 : S, l == 0 ? nullptr : mu[prv], l == 0 ? nullptr : var[prv],
+                                 l == 0 ? 1 : (int)(R / Rprev), l == 0 ? nullptr : samples[l], S, nullptr, R, 0,
+                                 mu[cur], var[cur], nullptr, nullptr, nullptr, nullptr, stream));
+    Rprev = R;
+  }
+  MomentArgs a;
+  a.n = n; a.S = S; a.tiled = fidelity >= 1 ? 1 : 0;
+  a.mu = mu[fidelity & 1]; a.var = var[fidelity & 1];
+  a.noise_lo = noise_lower; a.noise_hi = noise_upper; a.raw_noise = raw_noise;
+  a.out_mu = out_mu; a.out_var = out_var;
+  MOBO_LAUNCH("moment_kernel", st, moment_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a));
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int mobo_jes(const double* var_uncond, const double* var_cond, long long n, int accumulate, double* out,
+             void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n < 1) return 0;
+  MOBO_LAUNCH("jes_kernel", st,
+              jes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(var_uncond, var_cond, out, n, accumulate));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -43,10 +43,13 @@ struct PtrBatch3 {
 // ---------------------------------------------------------------------------------------------------
 // covariance function between inducing inputs
 // ---------------------------------------------------------------------------------------------------
-__global__ void kzz_kernel(LayerBatch b, double jitter, int block_index /* which ops block receives P */) {
+__global__ void kzz_kernel(LayerBatch b, double jitter, int block_index /* which ops block receives P */,
+                           int reset_counter /* zero finalize_kernel's arrival counter: ops is caller memory */) {
   __shared__ KernParams kp;
   const int bi = blockIdx.y;
   const int kind = b.kind[bi], d = b.d, M = b.M, MP = b.MP;
+  if (reset_counter && blockIdx.x == 0 && threadIdx.x == 0)
+    *reinterpret_cast<unsigned long long*>(b.ops[bi] + ops_scal(MP) + SC_COUNTER) = 0ull;
   const double* Zx = b.Zx[bi];
   const double* zf = b.zf[bi];
   if (threadIdx.x == 0) load_kern_params(kp, kind, d, b.theta[bi]);

@@ -1,0 +1,269 @@
+"""Fused ELBO step and Adam update: host mirror of ``mobo_elbo_step`` / ``mobo_adam`` (include/mobocmf_b200.h).
+
+``FusedELBOStep(model, elbo)(x_batch, y_batch, fidelities)`` is the body of ``_update_model``
+(``mobocmf/util/blackbox_mfdgp_fitter.py:161-168``) up to ``loss.backward()``: it returns ``(loss, kl_scaled)`` as device
+scalars and leaves d loss / d parameter in every trainable parameter's ``.grad`` (slices of one flat buffer, see
+``util.distributed.FlatGrads``) — one ctypes call, ~50 kernel launches, no host synchronisation, no torch autograd.
+``Adam`` is ``torch.optim.Adam`` (same defaults, same state names) on one multi-tensor kernel launch.
+
+The composable autograd path (``functional.py``) computes the same numbers through the same kernels; the fused path is
+used whenever its preconditions hold (``FusedELBOStep.supported``), there is no CPU fallback in either.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .util.distributed import FlatGrads
+
+MAX_LAYERS = 8
+MAX_THETA = 21
+_dp = ctypes.c_void_p
+
+
+class LayerDesc(ctypes.Structure):
+    _fields_ = [("Zx", _dp), ("raw_theta", _dp * MAX_THETA), ("g_raw_theta", _dp * MAX_THETA), ("m", _dp),
+                ("Lq", _dp), ("g_m", _dp), ("g_Lq", _dp), ("raw_noise", _dp), ("g_raw_noise", _dp),
+                ("noise_lower", ctypes.c_double), ("noise_upper", ctypes.c_double), ("eps", _dp)]
+
+
+class StepDesc(ctypes.Structure):
+    _fields_ = [("L", ctypes.c_int), ("d", ctypes.c_int), ("M", ctypes.c_int), ("S", ctypes.c_int),
+                ("B", ctypes.c_longlong), ("num_data", ctypes.c_longlong), ("jitter", ctypes.c_double),
+                ("x", _dp), ("y", _dp), ("fid", _dp), ("layer", LayerDesc * MAX_LAYERS), ("out", _dp),
+                ("workspace", _dp), ("accumulate", ctypes.c_int)]
+
+
+class AdamTensor(ctypes.Structure):
+    _fields_ = [("p", _dp), ("g", _dp), ("exp_avg", _dp), ("exp_avg_sq", _dp), ("n", ctypes.c_longlong)]
+
+
+def _bind():
+    return _lib.load()
+
+
+def _addr(t, index=0):
+    return t.data_ptr() + index * t.element_size()
+
+
+def _layer_raw_slots(layer):
+    """[(parameter, flat index)] of the RAW hyper-parameters in the kernels' theta order (include/mobocmf_b200.h):
+    layer 0 [a, l_0..]; layer >= 1 [a1, v_lin, a_f, l_f, a2, l1_0.., l2_0..]."""
+    cm = layer.covar_module
+    d = layer.x_dims
+    if layer.num_layer == 0:
+        return [(cm.raw_outputscale, 0)] + [(cm.base_kernel.raw_lengthscale, c) for c in range(d)]
+    k_x1, k_sum = cm.kernels[0].kernels
+    k_lin, k_f = k_sum.kernels
+    k_x2 = cm.kernels[1]
+    return ([(k_x1.raw_outputscale, 0), (k_lin.raw_variance, 0), (k_f.raw_outputscale, 0),
+             (k_f.base_kernel.raw_lengthscale, 0), (k_x2.raw_outputscale, 0)] +
+            [(k_x1.base_kernel.raw_lengthscale, c) for c in range(d)] +
+            [(k_x2.base_kernel.raw_lengthscale, c) for c in range(d)])
+
+
+class FusedELBOStep(object):
+    """One MFDGP's ELBO step on the fused kernel sequence."""
+
+    def __init__(self, model, elbo):
+        ok, why = self.supported(model)
+        if not ok:
+            raise RuntimeError("fused ELBO step not applicable: " + why)
+        self.model = model
+        self.elbo = elbo
+        self.lib = _bind()
+        self.L = model.num_hidden_layers
+        self.layers = [getattr(model, model.name_hidden_layer + str(i)) for i in range(self.L)]
+        self.liks = [getattr(model, model.name_hidden_layer_likelihood + str(i)) for i in range(self.L)]
+        self.M = self.layers[0].num_inducing
+        self.d = model.input_dims
+        self.device = self.layers[0]._Zx().device
+        self.out = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self.flat = None
+        self._ws = None
+        self._ws_key = None
+        self._desc = StepDesc()
+        self._sig = None
+
+    @staticmethod
+    def supported(model):
+        layers = [getattr(model, model.name_hidden_layer + str(i)) for i in range(model.num_hidden_layers)]
+        p = layers[0].variational_strategy._variational_distribution.variational_mean
+        if not p.is_cuda or p.dtype != torch.float64:
+            return False, "the model must hold fp64 CUDA parameters"
+        if model.use_only_highest_fidelity is True:
+            return False, "only-highest-fidelity models use per-layer inducing inputs"
+        if model.num_hidden_layers > MAX_LAYERS or model.input_dims > 8 or layers[0].num_inducing > 256:
+            return False, "shape outside the kernels' limits (L <= 8, d <= 8, M <= 256)"
+        z0 = layers[0]._Zx()
+        for lay in layers[1:]:
+            z = lay._Zx()
+            if z.shape != z0.shape or not bool(torch.equal(z, z0)):
+                return False, "layers do not share their inducing inputs"
+        return True, ""
+
+    # ---- descriptor -------------------------------------------------------------------------------------------
+    def _signature(self):
+        sig = []
+        for p in self.model.parameters():
+            sig.append((p.data_ptr(), p.requires_grad, None if p.grad is None else p.grad.data_ptr()))
+        return tuple(sig)
+
+    def _ensure_grads(self):
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        if self.flat is None or [id(p) for p in self.flat.params] != [id(p) for p in params]:
+            self.flat = FlatGrads(params)
+        elif not self.flat.attached():
+            self.flat.reattach()
+
+    def _build_desc(self):
+        D = self._desc
+        D.L, D.d, D.M = self.L, self.d, self.M
+        D.out = self.out.data_ptr()
+        D.accumulate = 0
+        D.jitter = float(self.layers[0].variational_strategy.jitter_val)
+        self._keep = []
+        for l, (layer, lik) in enumerate(zip(self.layers, self.liks)):
+            ld = D.layer[l]
+            zx = layer._Zx()
+            self._keep.append(zx)
+            ld.Zx = zx.data_ptr()
+            slots = _layer_raw_slots(layer)
+            for i in range(MAX_THETA):
+                if i < len(slots):
+                    p, idx = slots[i]
+                    ld.raw_theta[i] = _addr(p, idx)
+                    ld.g_raw_theta[i] = _addr(p.grad, idx) if p.requires_grad else None
+                else:
+                    ld.raw_theta[i] = None
+                    ld.g_raw_theta[i] = None
+            vd = layer.variational_strategy._variational_distribution
+            ld.m, ld.Lq = vd.variational_mean.data_ptr(), vd.chol_variational_covar.data_ptr()
+            ld.g_m = vd.variational_mean.grad.data_ptr() if vd.variational_mean.requires_grad else None
+            ld.g_Lq = vd.chol_variational_covar.grad.data_ptr() if vd.chol_variational_covar.requires_grad else None
+            rn = lik.noise_covar.raw_noise
+            ld.raw_noise = rn.data_ptr()
+            ld.g_raw_noise = rn.grad.data_ptr() if rn.requires_grad else None
+            c = lik.noise_covar.raw_noise_constraint
+            ld.noise_lower, ld.noise_upper = float(c.lower_bound), float(c.upper_bound)
+
+    def _prepare(self):
+        self._ensure_grads()
+        sig = self._signature()
+        if sig != self._sig:
+            for p in self.model.parameters():
+                if not p.is_contiguous():
+                    raise RuntimeError("mobocmf_b200: parameters must be contiguous")
+            self._build_desc()
+            self._sig = sig
+
+    def _workspace(self, B, S):
+        key = (B, S)
+        if self._ws_key != key:
+            n = self.lib.mobo_elbo_step_workspace_doubles(self.L, self.d, self.M, S, B)
+            self._ws = None
+            self._ws = torch.empty(n, dtype=torch.float64, device=self.device)
+            self._ws_key = key
+        return self._ws
+
+    def applies(self, x_batch):
+        """False when the minibatch equals the inducing inputs row for row: upstream then short-cuts layer 0 to
+        N(m, S) (quirk Q4), which only the composable path reproduces.  Costs a device sync only when B == M."""
+        return not (x_batch.shape[0] == self.M and bool(torch.equal(x_batch, self.layers[0]._Zx())))
+
+    # ---- the step ---------------------------------------------------------------------------------------------
+    def __call__(self, x_batch, y_batch, fidelities, eps=None, num_samples=1, accumulate=False):
+        """Returns (loss = -ELBO, KL * B / N) as 0-d device tensors (views of one result buffer, overwritten by the
+        next call) and writes the gradients.  ``eps``: optional list indexed by layer of the training normals
+        (B*S values for layers >= 1; reference: float32 ``torch.normal`` of shape (1, B), quirk Q6)."""
+        B = x_batch.shape[0]
+        S = int(num_samples)
+        if x_batch.shape[1] != self.d or y_batch.numel() != B or fidelities.numel() != B:
+            raise ValueError("x (B, d), y (B, 1), fidelities (B, 1) expected")
+        if not self.applies(x_batch):
+            raise RuntimeError("x_batch equals the inducing inputs (quirk Q4 shortcut): use the composable path")
+        self._prepare()
+        D = self._desc
+        x = x_batch.contiguous()
+        y = y_batch.contiguous()
+        f = fidelities.contiguous()
+        if not (x.is_cuda and x.dtype == torch.float64 and y.dtype == torch.float64 and f.dtype == torch.float64):
+            raise RuntimeError("mobocmf_b200 kernels need fp64 CUDA tensors (no CPU fallback)")
+        keep = [x, y, f]
+        for l in range(1, self.L):
+            e = None if eps is None else eps[l]
+            if e is None:
+                e = torch.randn(B * S, device=self.device, dtype=torch.float32)
+            e = e.to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
+            if e.numel() != B * S:
+                raise ValueError("eps[%d] must hold B * num_samples normals" % l)
+            keep.append(e)
+            D.layer[l].eps = e.data_ptr()
+        D.layer[0].eps = None
+        D.S, D.B, D.num_data = S, B, int(self.elbo.num_data)
+        D.x, D.y, D.fid = x.data_ptr(), y.data_ptr(), f.data_ptr()
+        D.workspace = self._workspace(B, S).data_ptr()
+        D.accumulate = 1 if accumulate else 0
+        _lib.check(self.lib.mobo_elbo_step(ctypes.byref(D), _lib.stream_ptr()), "mobo_elbo_step")
+        self._last_inputs = keep          # keep the step's inputs alive until the next call (async kernels)
+        for layer in self.layers:         # parameters are about to change: drop the composable path's cache
+            layer._ops_cache = None
+        return self.out[0], self.out[1]
+
+    def check(self):
+        """Synchronises and raises like upstream's NotPSDError / NanError when a Cholesky factorisation failed."""
+        st = float(self.out[3])
+        if st != 0.0:
+            raise RuntimeError("NotPSDError: K(Z, Z) + jitter I of layer %d is not positive definite" % (int(st) - 1))
+        if not bool(torch.isfinite(self.out[0])):
+            raise RuntimeError("NanError: the ELBO is not finite")
+
+
+class Adam(torch.optim.Optimizer):
+    """``torch.optim.Adam`` (defaults of ``mobocmf/util/blackbox_mfdgp_fitter.py:126,132,259``) with the update of all
+    parameters in ONE kernel launch (``mobo_adam``).  State keys match torch's (``step``, ``exp_avg``,
+    ``exp_avg_sq``) so ``state_dict`` round-trips with ``torch.optim.Adam``."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._table = None
+        self._sig = None
+
+    def zero_grad(self, set_to_none=False):
+        # gradients live in a persistent flat buffer that the fused step overwrites: keep the tensors
+        return super().zero_grad(set_to_none=set_to_none)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise NotImplementedError("closures are not used by the reference's training loops")
+        lib = _bind()
+        for group in self.param_groups:
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            for p in ps:
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                if not (p.is_cuda and p.dtype == torch.float64 and p.is_contiguous() and p.grad.is_contiguous()):
+                    raise RuntimeError("mobocmf_b200.Adam needs contiguous fp64 CUDA parameters (no CPU fallback)")
+            steps = {int(self.state[p]["step"]) for p in ps}
+            for step0 in sorted(steps):
+                sel = [p for p in ps if int(self.state[p]["step"]) == step0]
+                for i in range(0, len(sel), 64):
+                    chunk = sel[i:i + 64]
+                    arr = (AdamTensor * len(chunk))()
+                    for j, p in enumerate(chunk):
+                        st = self.state[p]
+                        arr[j].p, arr[j].g = p.data_ptr(), p.grad.data_ptr()
+                        arr[j].exp_avg, arr[j].exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+                        arr[j].n = p.numel()
+                    b1, b2 = group["betas"]
+                    _lib.check(lib.mobo_adam(len(chunk), arr, float(group["lr"]), float(b1), float(b2),
+                                             float(group["eps"]), step0 + 1, _lib.stream_ptr()), "mobo_adam")
+                for p in sel:
+                    self.state[p]["step"] = step0 + 1
+        return None

@@ -200,6 +200,8 @@ class MFDGP(nn.Module):
         S = self.num_samples_for_acquisition
         n = test_x.shape[0]
         x = test_x.contiguous()
+        if self._fused_acquisition_applies(x):
+            return self._predict_for_acquisition_fused(x, fidelity_layer)
         self.eval_mode()
         layer0 = getattr(self, self.name_hidden_layer + "0")
         mu, var = layer0._moments(x)                                    # identical for the S copies of a point
@@ -225,6 +227,54 @@ class MFDGP(nn.Module):
         mus = torch.mean(mus_tilde, 1)
         second_moment = torch.mean(vars_tilde + mus_tilde ** 2, 1)
         return mus, second_moment - mus ** 2
+
+    # ---- fused acquisition chain (mobo_acq_moments): no autograd graph, one enqueue per model ----
+    ACQ_CHUNK = 1 << 18      # candidates per enqueue (bounds the n * S scratch)
+
+    def _fused_acquisition_applies(self, x):
+        if self.training or self.use_only_highest_fidelity is True or not x.is_cuda or x.dtype != torch.float64:
+            return False
+        if torch.is_grad_enabled() and x.requires_grad:
+            return False                       # d acquisition / dX goes through the composable autograd path
+        layers = [getattr(self, self.name_hidden_layer + str(i)) for i in range(self.num_hidden_layers)]
+        for lay in layers[1:]:
+            lay._propagated_inducing_column()
+            if not lay._dev_cache.get("shared", False):
+                return False
+        return True
+
+    def _predict_for_acquisition_fused(self, x, fidelity_layer):
+        from .. import _lib
+        lib = _lib.load()
+        S = self.num_samples_for_acquisition
+        n, d = x.shape
+        layers = [getattr(self, self.name_hidden_layer + str(i)) for i in range(fidelity_layer + 1)]
+        with torch.no_grad():
+            trip = [lay.operators() for lay in layers]
+            ops = [t[0].detach() for t in trip]
+            theta = [t[1].detach().contiguous() for t in trip]
+            zf = [None if t[2] is None else t[2].detach().contiguous() for t in trip]
+            smp = [None] + [lay._samples_on(x.device) for lay in layers[1:]]
+            lik = getattr(self, self.name_hidden_layer_likelihood + str(fidelity_layer))
+            rn = lik.noise_covar.raw_noise
+            c = lik.noise_covar.raw_noise_constraint
+            key = ("noise_bounds", fidelity_layer)
+            if key not in layers[0]._dev_cache:
+                layers[0]._dev_cache[key] = (float(c.lower_bound), float(c.upper_bound))
+            lo, hi = layers[0]._dev_cache[key]
+            out_mu = torch.empty(n, dtype=torch.float64, device=x.device)
+            out_var = torch.empty(n, dtype=torch.float64, device=x.device)
+            chunk = min(n, self.ACQ_CHUNK)
+            scratch = torch.empty(4 * chunk * S, dtype=torch.float64, device=x.device)
+            M = layers[0].num_inducing
+            for a in range(0, n, chunk):
+                b = min(n, a + chunk)
+                _lib.check(lib.mobo_acq_moments(fidelity_layer, d, M, S, b - a, _lib.ptr(layers[0]._Zx()),
+                                                _lib.ptr_array(zf), _lib.ptr_array(theta), _lib.ptr_array(ops),
+                                                _lib.ptr_array(smp), _lib.ptr(rn), lo, hi, _lib.ptr(x[a:b]),
+                                                _lib.ptr(out_mu[a:b]), _lib.ptr(out_var[a:b]), _lib.ptr(scratch),
+                                                _lib.stream_ptr()), "mobo_acq_moments")
+        return out_mu, out_var
 
     def find_good_initial_inducing_points_and_values(self, x_train, y_train, fidelities, layer):
         """models/mfdgp.py:290-317, vectorised: nearest same-fidelity neighbour by the reference's expansion

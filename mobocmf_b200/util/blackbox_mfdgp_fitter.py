@@ -13,6 +13,7 @@ from copy import deepcopy
 import numpy as np
 import torch
 
+from ..fused import Adam
 from ..gp import settings
 from ..mlls.variational_elbo_mf import VariationalELBOMF
 from ..models.mfdgp import MFDGP, TL
@@ -116,10 +117,30 @@ class BlackBoxMFDGPFitter():
 
     # ---- the ELBO step (fitter.py:156-173) ----
     @staticmethod
+    def _fused_step(model, elbo):
+        """The fused kernel sequence for this (model, elbo) pair, or None when its preconditions do not hold
+        (only-HF models, per-layer inducing inputs); cached on the elbo object."""
+        cached = getattr(elbo, "_fused_step", None)
+        if cached is None:
+            from ..fused import FusedELBOStep
+            ok, _ = FusedELBOStep.supported(model)
+            cached = FusedELBOStep(model, elbo) if ok else False
+            elbo._fused_step = cached
+        return cached or None
+
+    @staticmethod
     def _update_model(model, elbo, optimizer, train_loader, eps=None):
         loss_iter = 0.0
         kl_iter = 0.0
+        fused = BlackBoxMFDGPFitter._fused_step(model, elbo)
         for (x_batch, y_batch, fidelities) in train_loader:
+            if fused is not None and fused.applies(x_batch):
+                # forward, ELBO and backward in one enqueue; gradients are overwritten, so no zero_grad
+                loss, kl = fused(x_batch, y_batch, fidelities, eps=eps)
+                optimizer.step()
+                loss_iter += loss.detach().clone()
+                kl_iter += kl.detach().clone()
+                continue
             with settings.num_likelihood_samples(1):
                 optimizer.zero_grad()
                 output = model(x_batch, eps=eps)
@@ -136,7 +157,7 @@ class BlackBoxMFDGPFitter():
             opts = []
             for h in handlers.values():
                 h.mfdgp.fix_variational_hypers(fix_variational_hypers)
-                opts.append(torch.optim.Adam([{'params': h.mfdgp.parameters()}], lr=lr))
+                opts.append(Adam([{'params': h.mfdgp.parameters()}], lr=lr))
             for n, (h, optimizer) in enumerate(zip(handlers.values(), opts)):
                 for i in range(num_epochs):
                     loss_iter, kl_iter = func_update_model(h.mfdgp, h.elbo, optimizer, h.train_loader)
@@ -239,7 +260,7 @@ class BlackBoxMFDGPFitter():
         for h in list(self.mfdgp_handlers_objs.values()) + list(self.mfdgp_handlers_cons.values()):
             h.mfdgp.fix_variational_hypers_cond(fix_variational_hypers)
             params = params + list(h.mfdgp.parameters())
-        optimizer = torch.optim.Adam([{'params': params}], lr=lr)
+        optimizer = Adam([{'params': params}], lr=lr)
         for i in range(num_iters):
             loss_iter = func_update_model(self.mfdgp_handlers_objs.values(), self.mfdgp_handlers_cons.values(),
                                           optimizer)
