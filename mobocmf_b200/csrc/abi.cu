@@ -51,7 +51,7 @@ size_t mobo_rows_save_doubles(int M, long long R) {
 
 size_t mobo_rows_bwd_work_doubles(int M, long long R) {
   const int MP = padded(M);
-  return (size_t)148 * 2 * (MAX_THETA + MP) + syrk_part_doubles(MP, R) + (size_t)syrk_nchunk(MP, R) * MP + 64;
+  return (size_t)256 * ROW_CTAS_PER_SM * (MAX_THETA + MP) + syrk_part_doubles(MP, R) + (size_t)syrk_nchunk(MP, R) * MP + 64;
 }
 
 size_t mobo_precompute_bwd_work_doubles(int M) {

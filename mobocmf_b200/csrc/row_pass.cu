@@ -11,16 +11,20 @@
 // which is the reference's  mean = m^T P^-1 k,  var = clamp(k_xx - |L_p^-1 k|^2, 0) + |L_q^T P^-1 k|^2.
 // K(Z_l, X) lives only in shared memory (it is written to HBM only when the backward needs it).
 //
-// Tile: 64 rows x MP inducing points per CTA, 16 warps.  The two triangular M x M products run on the DMMA pipe
-// (mma.sync.m8n8k4.f64); each warp owns two 16-row slabs (p, ns-1-p) of the triangular operator so that the
-// triangular work is balanced, and streams its slab of the operator from L2 straight into A fragments.
+// Tile: 32 rows x MP inducing points per CTA, 8 warps, two CTAs per SM (so that one CTA's covariance build on the
+// DFMA side overlaps the other's products; DMMA and DFMA share the FP64 pipe, profiles/r01c_fp64_probe_*.log, so
+// the gain is in the barriers and pipeline drains, not in the arithmetic).  The two triangular M x M products run on
+// the DMMA pipe (mma.sync.m8n8k4.f64); each warp owns two 16-row slabs (p, ns-1-p) of the triangular operator so
+// that the triangular work is balanced, and streams its slab of the operator from L2 straight into A fragments.
 #include "common.cuh"
 
 namespace mobo {
 
-constexpr int TR = 64;             // rows per tile
-constexpr int ROW_THREADS = 512;   // 16 warps
+constexpr int TR = 32;             // rows per tile
+constexpr int ROW_THREADS = 256;   // 8 warps: one per pair of 16-row operator slabs at MP = 256
 constexpr int ROW_WARPS = ROW_THREADS / 32;
+constexpr int NHALF = TR / 32;     // 32-column groups of the tile; warps = NHALF x (MP / 32) slab pairs
+constexpr int ROW_CTAS_PER_SM = 2; // two CTAs per SM fill each other's phase boundaries (K build <-> DMMA products)
 constexpr int MAX_MP = 256;        // slab scheme: (MP/32) warp pairs <= 8
 constexpr int NCH_MAX = MAX_MP / 32;
 constexpr int MAX_THETA = 5 + 2 * kMaxD;
@@ -59,8 +63,43 @@ struct RowArgs {
   int want_x_grads;
 };
 
+// Covariance parameters in the form the row kernels evaluate them: every exponential is 2^y with the -1/2 log2(e) / l^2
+// factors folded into the coefficients and log2 of the amplitude folded into the exponent, so
+//   kind 0: k = 2^(la1 + sum_c c1_c (x_c - z_c)^2)
+//   kind 1: k = 2^(la1 + sum_c c1_c D_c^2) * (v f f' + 2^(laf + cf (f - f')^2)) + 2^(la2 + sum_c c2_c D_c^2)
+struct KernFast {
+  int kind, d;
+  double la1, laf, la2, vlin, cf, ilf;
+  double a1, af, a2, lf;
+  double c1[kMaxD], c2[kMaxD];     // -0.5 log2(e) / l^2
+  double il1[kMaxD], il2[kMaxD];   // 1 / l^2
+};
+
+constexpr double kExp2Magic = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to the nearest integer
+constexpr int kExp2TabBits = 6, kExp2Tab = 1 << kExp2TabBits;
+
+// 2^y for y <= ~1000 to ~1.5 ulp: y = n / 64 + r, |r| <= 1/128; 2^y = 2^(n >> 6) * tab[n & 63] * p5(r).
+// 10 FP64-pipe operations against ~22 for libdevice exp(); the row kernels evaluate 3 of these per (row, inducing
+// point) pair, and DFMA shares the FP64 pipe with the DMMA products (profiles/r01c_fp64_probe_*.log).
+__device__ __forceinline__ double exp2_tab(double y, const double* __restrict__ tab) {
+  y = fmax(y, -1000.0);                                 // below this the result is 0 for every purpose here
+  const double t = fma(y, (double)kExp2Tab, kExp2Magic);
+  const int n = __double2loint(t);
+  const double nf = t - kExp2Magic;
+  const double r = fma(nf, -1.0 / kExp2Tab, y);         // exact
+  double p = 1.3333558146428443e-3;                      // ln2^5 / 5!
+  p = fma(p, r, 9.618129107628477e-3);                   // ln2^4 / 4!
+  p = fma(p, r, 5.550410866482158e-2);                   // ln2^3 / 3!
+  p = fma(p, r, 2.402265069591007e-1);                   // ln2^2 / 2!
+  p = fma(p, r, 6.931471805599453e-1);                   // ln2
+  p = fma(p, r, 1.0);
+  const double res = tab[n & (kExp2Tab - 1)] * p;
+  return __hiloint2double(__double2hiint(res) + ((n >> kExp2TabBits) << 20), __double2loint(res));
+}
+
 struct RowSmem {
-  KernParams kp;
+  KernFast kf;
+  double e2tab[kExp2Tab];
   double red[3][NCH_MAX][TR];     // per warp-pair partial column sums: q1, mu, q2
   double xs[TR][kMaxD];
   double fs[TR];
@@ -181,13 +220,34 @@ __device__ __forceinline__ void load_tile_rows(const RowArgs& a, RowSmem& sm, lo
       }
     }
     sm.fs[tid] = f;
-    sm.kxx[tid] = kern_diag(sm.kp, f);
+    sm.kxx[tid] = sm.kf.kind == 0 ? sm.kf.a1 : sm.kf.a1 * (sm.kf.vlin * f * f + sm.kf.af) + sm.kf.a2;
+  }
+}
+
+__device__ inline void load_kern_fast(KernFast& kf, int kind, int d, const double* __restrict__ theta) {
+  const double nhl2e = -0.5 * 1.4426950408889634074;     // -1/2 log2(e)
+  kf.kind = kind; kf.d = d;
+  for (int c = 0; c < kMaxD; ++c) { kf.c1[c] = 0.0; kf.c2[c] = 0.0; kf.il1[c] = 0.0; kf.il2[c] = 0.0; }
+  if (kind == 0) {
+    kf.a1 = theta[0]; kf.la1 = log2(kf.a1);
+    kf.vlin = 0.0; kf.af = 0.0; kf.a2 = 0.0; kf.laf = -INFINITY; kf.la2 = -INFINITY; kf.cf = 0.0; kf.ilf = 0.0; kf.lf = 1.0;
+    for (int c = 0; c < d; ++c) { const double l = theta[1 + c]; kf.il1[c] = 1.0 / (l * l); kf.c1[c] = nhl2e * kf.il1[c]; }
+  } else {
+    kf.a1 = theta[0]; kf.vlin = theta[1]; kf.af = theta[2]; kf.lf = theta[3]; kf.a2 = theta[4];
+    kf.la1 = log2(kf.a1); kf.laf = log2(kf.af); kf.la2 = log2(kf.a2);
+    kf.ilf = 1.0 / (kf.lf * kf.lf); kf.cf = nhl2e * kf.ilf;
+    for (int c = 0; c < d; ++c) {
+      const double l1 = theta[5 + c], l2 = theta[5 + d + c];
+      kf.il1[c] = 1.0 / (l1 * l1); kf.il2[c] = 1.0 / (l2 * l2);
+      kf.c1[c] = nhl2e * kf.il1[c]; kf.c2[c] = nhl2e * kf.il2[c];
+    }
   }
 }
 
 __device__ __forceinline__ void load_inducing(const RowArgs& a, RowSmem& sm) {
   const int tid = threadIdx.x;
-  if (tid == 0) load_kern_params(sm.kp, a.kind, a.d, a.theta);
+  if (tid == 0) load_kern_fast(sm.kf, a.kind, a.d, a.theta);
+  if (tid >= 32 && tid < 32 + kExp2Tab) sm.e2tab[tid - 32] = exp2((double)(tid - 32) / kExp2Tab);
   for (int idx = tid; idx < a.MP * a.d; idx += ROW_THREADS) {
     const int j = idx / a.d, c = idx - j * a.d;
     sm.zsT[c][j] = j < a.M ? a.Zx[(size_t)j * a.d + c] : 0.0;
@@ -195,35 +255,84 @@ __device__ __forceinline__ void load_inducing(const RowArgs& a, RowSmem& sm) {
   for (int j = tid; j < a.MP; j += ROW_THREADS) sm.zfs[j] = (a.kind == 1 && j < a.M) ? a.zf[j] : 0.0;
 }
 
-__device__ __forceinline__ double kern_pair(const RowSmem& sm, int r, int j) {
-  const KernParams& kp = sm.kp;
-  double D1 = 0.0, D2 = 0.0;
-  for (int c = 0; c < kp.d; ++c) {
-    const double df = sm.xs[r][c] - sm.zsT[c][j];
-    const double d2 = df * df;
-    D1 = fma(d2, kp.il1[c], D1);
-    D2 = fma(d2, kp.il2[c], D2);
+constexpr int RPW = TR / ROW_WARPS;   // tile rows per warp in the covariance phases
+
+// K(Z_l, rows of the tile) into shared memory: Ks[r][j].  Warp <-> RPW rows, lane <-> inducing point of a 32-chunk;
+// the inducing point stays in registers while the warp's rows (kept in registers too) run past it, which gives RPW
+// independent exponent chains per thread.
+template <int KIND, int D>
+__device__ __forceinline__ void build_k_tile(const RowSmem& sm, double* __restrict__ Ks, int ldb, int M, int MP,
+                                             int nvalid, int warp, int lane) {
+  const KernFast& kf = sm.kf;
+  const double* tab = sm.e2tab;
+  const int rbase = warp * RPW;
+  double x[RPW][D], f[RPW], vf[RPW], c1[D], c2[D];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) x[i][c] = sm.xs[rbase + i][c];
+    f[i] = sm.fs[rbase + i];
+    vf[i] = kf.vlin * f[i];
   }
-  const double E1 = exp(-0.5 * D1);
-  if (kp.kind == 0) return kp.a1 * E1;
-  const double f = sm.fs[r], zf = sm.zfs[j];
-  const double dff = f - zf;
-  const double Ef = exp(-0.5 * dff * dff * kp.ilf);
-  const double E2 = exp(-0.5 * D2);
-  return kp.a1 * E1 * (kp.vlin * f * zf + kp.af * Ef) + kp.a2 * E2;
+#pragma unroll
+  for (int c = 0; c < D; ++c) { c1[c] = kf.c1[c]; c2[c] = kf.c2[c]; }
+  const double la1 = kf.la1, la2 = kf.la2, laf = kf.laf, cf = kf.cf;
+  for (int ch = 0; ch < MP / 32; ++ch) {
+    const int j = 32 * ch + lane;
+    double z[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) z[c] = sm.zsT[c][j];
+    const double zf = sm.zfs[j];
+    const bool jok = j < M;
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      double D1 = la1, D2 = la2;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double df = x[i][c] - z[c];
+        const double d2 = df * df;
+        D1 = fma(d2, c1[c], D1);
+        if (KIND == 1) D2 = fma(d2, c2[c], D2);
+      }
+      double k;
+      if (KIND == 0) {
+        k = exp2_tab(D1, tab);
+      } else {
+        const double dff = f[i] - zf;
+        const double Ef = exp2_tab(fma(dff * dff, cf, laf), tab);
+        k = fma(exp2_tab(D1, tab), fma(vf[i], zf, Ef), exp2_tab(D2, tab));
+      }
+      Ks[(size_t)(rbase + i) * ldb + j] = (jok && rbase + i < nvalid) ? k : 0.0;
+    }
+  }
 }
 
-__global__ void __launch_bounds__(ROW_THREADS, 1) row_fwd_kernel(const __grid_constant__ RowArgs a) {
+template <int KIND>
+__device__ __forceinline__ void build_k_tile_d(const RowSmem& sm, double* Ks, int ldb, int M, int MP, int nvalid,
+                                               int warp, int lane) {
+  switch (sm.kf.d) {
+    case 1: build_k_tile<KIND, 1>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    case 2: build_k_tile<KIND, 2>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    case 3: build_k_tile<KIND, 3>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    case 4: build_k_tile<KIND, 4>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    case 5: build_k_tile<KIND, 5>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    case 6: build_k_tile<KIND, 6>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    case 7: build_k_tile<KIND, 7>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    default: build_k_tile<KIND, 8>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+  }
+}
+
+__global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(const __grid_constant__ RowArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RowSmem& sm = *reinterpret_cast<RowSmem*>(smem_raw);
   double* Ks = tile_ptr(smem_raw);
   const int MP = a.MP, ldb = MP + 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int half = warp & 1, p = warp >> 1;
+  const int half = warp % NHALF, p = warp / NHALF;
   const int npairs = MP / 32, ns = MP / 16;
   const bool active = p < npairs;
   const int sA = p, sB = ns - 1 - p;
-  const int nact = 2 * npairs, wact = p * 2 + half;
+  const int nact = NHALF * npairs, wact = p * NHALF + half;
   const int g = lane >> 2, t = lane & 3;
   const double* W = a.ops + ops_block(MP, OPS_W);
   const double* G = a.ops + ops_block(MP, OPS_HT);
@@ -239,10 +348,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_fwd_kernel(const __grid_co
     load_tile_rows(a, sm, row0, nvalid);
     __syncthreads();
     // ---- K(Z_l, rows) into shared memory ----
-    for (int idx = tid; idx < TR * MP; idx += ROW_THREADS) {
-      const int r = idx / MP, j = idx - r * MP;
-      Ks[(size_t)r * ldb + j] = (j < a.M && r < nvalid) ? kern_pair(sm, r, j) : 0.0;
-    }
+    if (a.kind == 0) build_k_tile_d<0>(sm, Ks, ldb, a.M, MP, nvalid, warp, lane);
+    else build_k_tile_d<1>(sm, Ks, ldb, a.M, MP, nvalid, warp, lane);
     __syncthreads();
     // ---- t = W k ----
     double acc[2][2][4][2];
@@ -288,10 +395,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_fwd_kernel(const __grid_co
     if (active) store_acc_to_tile(acc, Ks, ldb, sA, sB, half, lane);
     __syncthreads();
     if (a.Tsave) {     // whitened rows t = W k, row-major [R][MP], for the backward (SYRK statistics and dt)
-      for (int idx = tid; idx < nvalid * MP; idx += ROW_THREADS) {
-        const int r = idx / MP, j = idx - r * MP;
-        a.Tsave[(size_t)(row0 + r) * MP + j] = Ks[(size_t)r * ldb + j];
-      }
+      for (int r = warp; r < nvalid; r += ROW_WARPS)
+        for (int j = lane; j < MP; j += 32) a.Tsave[(size_t)(row0 + r) * MP + j] = Ks[(size_t)r * ldb + j];
     }
     // ---- u = H^T t ----
     if (active) {
@@ -331,6 +436,155 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_fwd_kernel(const __grid_co
   }
 }
 
+// Backward through the covariance function for one tile: Ks holds dk = d loss / d K(z_j, row r).  Same thread mapping
+// as build_k_tile (warp <-> RPW rows, lane <-> inducing point).  Accumulator conventions (undone at the final flush):
+//   th[0] = sum gk a1 E1 gg  (d/da1 = th[0] / a1)     th[1] = sum gk a1 E1 f f'   (d/dv)
+//   th[2] = sum gk a1 E1 af Ef (d/daf = th[2] / af)   th[3] = sum gk a1 E1 af Ef (f-f')^2  (d/dlf = th[3] / lf^3)
+//   th[4] = sum gk a2 E2     (d/da2 = th[4] / a2)     tl1[c], tl2[c] = sum g D_c^2  (d/dl_c = tl / l_c^3)
+template <int KIND, int D, bool PARAM, bool XGRAD>
+__device__ __forceinline__ void kgrad_tile(const RowArgs& a, RowSmem& sm, const double* __restrict__ Ks, int ldb,
+                                           long long row0, int nvalid, int warp, int lane) {
+  const KernFast& kf = sm.kf;
+  const double* tab = sm.e2tab;
+  const int M = a.M, nch = a.MP / 32;
+  const int rbase = warp * RPW;
+  double f[RPW], vf[RPW], c1[D], c2[D];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) { f[i] = sm.fs[rbase + i]; vf[i] = kf.vlin * f[i]; }
+#pragma unroll
+  for (int c = 0; c < D; ++c) { c1[c] = kf.c1[c]; c2[c] = kf.c2[c]; }
+  const double la1 = kf.la1, la2 = kf.la2, laf = kf.laf, cf = kf.cf, vlin = kf.vlin, ilf = kf.ilf;
+  double th[5], tl1[D], tl2[D], rdf[RPW], rdx[XGRAD ? RPW : 1][D];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) th[q] = 0.0;
+#pragma unroll
+  for (int c = 0; c < D; ++c) { tl1[c] = 0.0; tl2[c] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) rdf[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < (XGRAD ? RPW : 1); ++i)
+#pragma unroll
+    for (int c = 0; c < D; ++c) rdx[i][c] = 0.0;
+
+  for (int ch = 0; ch < nch; ++ch) {
+    const int j = 32 * ch + lane;
+    double z[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) z[c] = sm.zsT[c][j];
+    const double zf = sm.zfs[j], vz = vlin * zf;
+    const bool jok = j < M;
+    double azf = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const double gk = jok ? Ks[(size_t)(rbase + i) * ldb + j] : 0.0;
+      double diff[D], d2[D], D1 = la1, D2 = la2;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        diff[c] = sm.xs[rbase + i][c] - z[c];
+        d2[c] = diff[c] * diff[c];
+        D1 = fma(d2[c], c1[c], D1);
+        if (KIND == 1) D2 = fma(d2[c], c2[c], D2);
+      }
+      if (KIND == 0) {
+        const double g1 = gk * exp2_tab(D1, tab);
+        if (PARAM) {
+          th[0] += g1;
+#pragma unroll
+          for (int c = 0; c < D; ++c) tl1[c] = fma(g1, d2[c], tl1[c]);
+        }
+        if (XGRAD) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) rdx[i][c] = fma(-g1 * diff[c], kf.il1[c], rdx[i][c]);
+        }
+      } else {
+        const double dff = f[i] - zf, dff2 = dff * dff;
+        const double Efp = exp2_tab(fma(dff2, cf, laf), tab);        // af Ef
+        const double s1 = exp2_tab(D1, tab), s2 = exp2_tab(D2, tab);  // a1 E1, a2 E2
+        const double fz = f[i] * zf;
+        const double gg = fma(vlin, fz, Efp);                         // k_lin + k_f
+        const double gs1 = gk * s1, g2 = gk * s2;
+        const double g1 = gs1 * gg, gEf = gs1 * Efp;
+        const double q = gEf * (dff * ilf);                           // gk a1 E1 af Ef (f - f') / lf^2
+        rdf[i] += fma(gs1, vz, -q);
+        if (PARAM) {
+          azf += fma(gs1, vf[i], q);
+          th[0] += g1;
+          th[1] = fma(gs1, fz, th[1]);
+          th[2] += gEf;
+          th[3] = fma(gEf, dff2, th[3]);
+          th[4] += g2;
+#pragma unroll
+          for (int c = 0; c < D; ++c) { tl1[c] = fma(g1, d2[c], tl1[c]); tl2[c] = fma(g2, d2[c], tl2[c]); }
+        }
+        if (XGRAD) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) rdx[i][c] -= diff[c] * fma(g1, kf.il1[c], g2 * kf.il2[c]);
+        }
+      }
+    }
+    if (PARAM && KIND == 1) sm.acc_zf[warp][j] += azf;   // one owner per slot -> deterministic
+  }
+  // row-wise sums over the inducing points, and the diag term d k_xx of the variance
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int r = rbase + i;
+    const bool rok = r < nvalid;
+    const double dvm = sm.dvar[r] * sm.mask[r];
+    if (KIND == 1) {
+      const double sdf = warp_sum(rdf[i]);
+      if (lane == 0 && rok) a.df[row0 + r] = sdf + dvm * 2.0 * kf.a1 * vlin * f[i];
+    }
+    if (XGRAD) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double sx = warp_sum(rdx[i][c]);
+        if (lane == 0 && rok) a.dxrow[(size_t)(row0 + r) * D + c] = sx;
+      }
+    }
+    if (PARAM && lane == 0) {
+      if (KIND == 0) {
+        th[0] += dvm * kf.a1;
+      } else {
+        th[0] += dvm * kf.a1 * fma(vlin * f[i], f[i], kf.af);
+        th[1] += dvm * kf.a1 * f[i] * f[i];
+        th[2] += dvm * kf.a1 * kf.af;
+        th[4] += dvm * kf.a2;
+      }
+    }
+  }
+  if (PARAM) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const double red = warp_sum(th[q]);
+      if (lane == 0) sm.acc_th[warp][q] += red;
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      double red = warp_sum(tl1[c]);
+      if (lane == 0) sm.acc_th[warp][5 + c] += red;
+      if (KIND == 1) {
+        red = warp_sum(tl2[c]);
+        if (lane == 0) sm.acc_th[warp][5 + kMaxD + c] += red;
+      }
+    }
+  }
+}
+
+template <int KIND, bool PARAM, bool XGRAD>
+__device__ __forceinline__ void kgrad_tile_d(const RowArgs& a, RowSmem& sm, const double* Ks, int ldb, long long row0,
+                                             int nvalid, int warp, int lane) {
+  switch (sm.kf.d) {
+    case 1: kgrad_tile<KIND, 1, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 2: kgrad_tile<KIND, 2, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 3: kgrad_tile<KIND, 3, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 4: kgrad_tile<KIND, 4, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 5: kgrad_tile<KIND, 5, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 6: kgrad_tile<KIND, 6, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 7: kgrad_tile<KIND, 7, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    default: kgrad_tile<KIND, 8, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // backward of the row pass: given d loss/d mu_r, d loss/d var_r
 //   dt = dmu beta - 2 dvar (mask t - H u);  dk = W^T dt
@@ -339,29 +593,27 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_fwd_kernel(const __grid_co
 // are accumulated by syrk_kernel from the saved T and consumed by the operator backward (matrix_ops.cu).
 // ---------------------------------------------------------------------------------------------------
 template <bool PARAM, bool XGRAD>
-__global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_kernel(const __grid_constant__ RowArgs a) {
+__global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_bwd_kernel(const __grid_constant__ RowArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RowSmem& sm = *reinterpret_cast<RowSmem*>(smem_raw);
   double* Ks = tile_ptr(smem_raw);
   const int MP = a.MP, ldb = MP + 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int half = warp & 1, p = warp >> 1;
+  const int half = warp % NHALF, p = warp / NHALF;
   const int npairs = MP / 32, ns = MP / 16;
   const bool active = p < npairs;
   const int sA = p, sB = ns - 1 - p;
-  const int nact = 2 * npairs, wact = p * 2 + half;
+  const int nact = NHALF * npairs, wact = p * NHALF + half;
   const int g = lane >> 2, t = lane & 3;
   const double* WT = a.ops + ops_block(MP, OPS_WT);
   const double* H = a.ops + ops_block(MP, OPS_H);
   const double* beta = a.ops + ops_beta(MP);
-  const int nch = MP / 32;
   const int d = a.d;
 
   load_inducing(a, sm);
   for (int j = lane; j < MAX_MP; j += 32) sm.acc_zf[warp][j] = 0.0;
   if (lane < MAX_THETA) sm.acc_th[warp][lane] = 0.0;
   __syncthreads();
-  const KernParams& kp = sm.kp;
 
   const long long ntiles = (a.R + TR - 1) / TR;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -387,10 +639,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_kernel(const __grid_co
       slab_gemm<false>(acc, H, MP, Ks, ldb, sA, sB, half, lane);
     }
     __syncthreads();   // u is no longer needed: stage the saved t tile through shared memory
-    for (int idx = tid; idx < TR * MP; idx += ROW_THREADS) {
-      const int r = idx / MP, j = idx - r * MP;
-      Ks[(size_t)r * ldb + j] = r < nvalid ? a.Tsave[(size_t)(row0 + r) * MP + j] : 0.0;
-    }
+    for (int r = warp; r < TR; r += ROW_WARPS)
+      for (int j = lane; j < MP; j += 32)
+        Ks[(size_t)r * ldb + j] = r < nvalid ? a.Tsave[(size_t)(row0 + r) * MP + j] : 0.0;
     __syncthreads();
     if (active) {
 #pragma unroll
@@ -420,123 +671,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_kernel(const __grid_co
     __syncthreads();
     if (active) store_acc_to_tile(acc, Ks, ldb, sA, sB, half, lane);
     __syncthreads();
-    // ---- through the covariance function: warp <-> rows, lanes <-> inducing points of a 32-chunk ----
-    double th_s[5], th_l1[kMaxD], th_l2[kMaxD], azf[NCH_MAX];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) th_s[i] = 0.0;
-#pragma unroll
-    for (int c = 0; c < kMaxD; ++c) { th_l1[c] = 0.0; th_l2[c] = 0.0; }
-#pragma unroll
-    for (int ch = 0; ch < NCH_MAX; ++ch) azf[ch] = 0.0;
-    for (int r = warp; r < nvalid; r += ROW_WARPS) {
-      const double f = sm.fs[r];
-      double rdf = 0.0;
-      double rdx[kMaxD];
-#pragma unroll
-      for (int c = 0; c < kMaxD; ++c) rdx[c] = 0.0;
-#pragma unroll
-      for (int ch = 0; ch < NCH_MAX; ++ch) {
-        const int j = 32 * ch + lane;
-        if (ch < nch && j < a.M) {
-          const double gk = Ks[(size_t)r * ldb + j];
-          double D1 = 0.0, D2 = 0.0;
-          double diff[kMaxD];
-#pragma unroll
-          for (int c = 0; c < kMaxD; ++c) {
-            diff[c] = c < d ? sm.xs[r][c] - sm.zsT[c][j] : 0.0;
-            const double d2 = diff[c] * diff[c];
-            D1 = fma(d2, kp.il1[c], D1);
-            D2 = fma(d2, kp.il2[c], D2);
-          }
-          const double E1 = exp(-0.5 * D1);
-          if (kp.kind == 0) {
-            const double gkk = gk * kp.a1 * E1;
-            if (PARAM) {
-              th_s[0] = fma(gk, E1, th_s[0]);
-#pragma unroll
-              for (int c = 0; c < kMaxD; ++c) th_l1[c] = fma(gkk, diff[c] * diff[c], th_l1[c]);
-            }
-            if (XGRAD) {
-#pragma unroll
-              for (int c = 0; c < kMaxD; ++c) rdx[c] = fma(-gkk * diff[c], kp.il1[c], rdx[c]);
-            }
-          } else {
-            const double zf = sm.zfs[j];
-            const double dff = f - zf;
-            const double Ef = exp(-0.5 * dff * dff * kp.ilf);
-            const double E2 = exp(-0.5 * D2);
-            const double gg = kp.vlin * f * zf + kp.af * Ef;   // k_lin + k_f
-            const double s1 = kp.a1 * E1, s2 = kp.a2 * E2;
-            const double dEf = s1 * kp.af * Ef * dff * kp.ilf;  // s1 af Ef (f - zf) / lf^2
-            rdf = fma(gk, s1 * kp.vlin * zf - dEf, rdf);
-            const double g1 = gk * s1 * gg, g2 = gk * s2;
-            if (PARAM) {
-              azf[ch] = fma(gk, s1 * kp.vlin * f + dEf, azf[ch]);
-              th_s[0] = fma(gk, E1 * gg, th_s[0]);          // a1
-              th_s[1] = fma(gk, s1 * f * zf, th_s[1]);      // v
-              th_s[2] = fma(gk, s1 * Ef, th_s[2]);          // af
-              th_s[3] = fma(gk, dEf * dff, th_s[3]);        // lf (x 1/lf applied at flush)
-              th_s[4] = fma(gk, E2, th_s[4]);               // a2
-#pragma unroll
-              for (int c = 0; c < kMaxD; ++c) {
-                const double d2 = diff[c] * diff[c];
-                th_l1[c] = fma(g1, d2, th_l1[c]);           // (x 1/l^3 applied at flush)
-                th_l2[c] = fma(g2, d2, th_l2[c]);
-              }
-            }
-            if (XGRAD) {
-#pragma unroll
-              for (int c = 0; c < kMaxD; ++c) rdx[c] -= diff[c] * (g1 * kp.il1[c] + g2 * kp.il2[c]);
-            }
-          }
-        }
-      }
-      // row-wise sums over the inducing points
-      const double dvm = sm.dvar[r] * sm.mask[r];
-      if (kp.kind == 1) {
-        rdf = warp_sum(rdf);
-        if (lane == 0) a.df[row0 + r] = rdf + dvm * 2.0 * kp.a1 * kp.vlin * f;   // + d k_xx / d f
-      }
-      if (XGRAD) {
-#pragma unroll
-        for (int c = 0; c < kMaxD; ++c)
-          if (c < d) {
-            const double s = warp_sum(rdx[c]);
-            if (lane == 0) a.dxrow[(size_t)(row0 + r) * d + c] = s;
-          }
-      }
-      // d k_xx / d theta (diag term of the variance), added once per row by lane 0
-      if (PARAM && lane == 0) {
-        if (kp.kind == 0) {
-          th_s[0] += dvm;
-        } else {
-          th_s[0] += dvm * (kp.vlin * f * f + kp.af);
-          th_s[1] += dvm * kp.a1 * f * f;
-          th_s[2] += dvm * kp.a1;
-          th_s[4] += dvm;
-        }
-      }
-    }
-    if (PARAM) {
-      // per-warp accumulators in shared memory (each slot has one owner -> deterministic)
-#pragma unroll
-      for (int ch = 0; ch < NCH_MAX; ++ch)
-        if (ch < nch) sm.acc_zf[warp][32 * ch + lane] += azf[ch];
-      double red;
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        red = warp_sum(th_s[i]);
-        if (lane == 0) sm.acc_th[warp][i] += red;
-      }
-#pragma unroll
-      for (int c = 0; c < kMaxD; ++c)
-        if (c < d) {
-          red = warp_sum(th_l1[c]);
-          if (lane == 0) sm.acc_th[warp][5 + c] += red;
-          red = warp_sum(th_l2[c]);
-          if (lane == 0) sm.acc_th[warp][5 + kMaxD + c] += red;
-        }
-    }
+    // ---- through the covariance function ----
+    if (a.kind == 0) kgrad_tile_d<0, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane);
+    else kgrad_tile_d<1, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane);
     __syncthreads();
   }
   if (PARAM) {
@@ -550,19 +687,27 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_kernel(const __grid_co
     if (tid < MAX_THETA) {
       double s = 0.0;
       for (int w = 0; w < ROW_WARPS; ++w) s += sm.acc_th[w][tid];
-      // map (scalars | l1 | l2) accumulators to the theta layout and apply the 1/l^3 factors
+      // map (scalars | l1 | l2) accumulators to the theta layout and undo the accumulator scalings (see kgrad_tile)
+      const KernFast& kf = sm.kf;
       double out = 0.0;
       int slot = -1;
-      if (kp.kind == 0) {
-        if (tid == 0) { slot = 0; out = s; }
-        else if (tid >= 5 && tid < 5 + d) { slot = 1 + (tid - 5); out = s * kp.il1[tid - 5] * sqrt(kp.il1[tid - 5]); }
+      if (kf.kind == 0) {
+        if (tid == 0) { slot = 0; out = kf.a1 > 0.0 ? s / kf.a1 : 0.0; }
+        else if (tid >= 5 && tid < 5 + d) { slot = 1 + (tid - 5); out = s * kf.il1[tid - 5] * sqrt(kf.il1[tid - 5]); }
       } else {
-        if (tid < 5) { slot = tid; out = tid == 3 ? s * sqrt(kp.ilf) : s; }
-        else if (tid < 5 + d) { slot = tid; out = s * kp.il1[tid - 5] * sqrt(kp.il1[tid - 5]); }
+        if (tid < 5) {
+          slot = tid;
+          if (tid == 0) out = kf.a1 > 0.0 ? s / kf.a1 : 0.0;
+          else if (tid == 1) out = s;
+          else if (tid == 2) out = kf.af > 0.0 ? s / kf.af : 0.0;
+          else if (tid == 3) out = s * kf.ilf / kf.lf;
+          else out = kf.a2 > 0.0 ? s / kf.a2 : 0.0;
+        }
+        else if (tid < 5 + d) { slot = tid; out = s * kf.il1[tid - 5] * sqrt(kf.il1[tid - 5]); }
         else if (tid >= 5 + kMaxD && tid < 5 + kMaxD + d) {
           const int c = tid - 5 - kMaxD;
           slot = 5 + d + c;
-          out = s * kp.il2[c] * sqrt(kp.il2[c]);
+          out = s * kf.il2[c] * sqrt(kf.il2[c]);
         }
       }
       if (slot >= 0) a.part_theta[(size_t)blockIdx.x * MAX_THETA + slot] = out;
@@ -581,101 +726,145 @@ __global__ void reduce_partials_kernel(const double* __restrict__ part, int nblo
 }
 
 // ---------------------------------------------------------------------------------------------------
-// A2 = sum_r w_r t_r t_r^T (lower 64x64 tiles) from the saved whitened rows T [R][MP]; split over row chunks, partial
-// tiles reduced in a fixed order by syrk_reduce_kernel which also mirrors to the full symmetric matrix.
-// w_r = dvar_r (which = 0) or dvar_r * [clamped row] (which = 1, only when some row was clamped).
+// A2 = sum_r w_r t_r t_r^T from the saved whitened rows T [R][MP] (the SYRK of the backward).
+// The lower triangle is cut into 32 x 32 blocks (36 at MP = 256), one block per warp, 12 warps per CTA, so every
+// DMMA is useful work and every warp carries the same load.  A CTA streams ALL MP columns of its chunk of rows
+// through a 3-stage cp.async pipeline (32 rows per stage) and each warp reads its two column panels from there.
+// Partial blocks per row chunk are folded in chunk order by syrk_reduce_kernel, which also mirrors the result to
+// the full symmetric matrix.  w_r = dvar_r (which = 0) or dvar_r * [clamped row] (which = 1, skipped unless some
+// row was clamped).  Group 0 also accumulates b = sum_r dmu_r t_r.
 // ---------------------------------------------------------------------------------------------------
-constexpr int SY_T = 64, SY_K = 32, SY_THREADS = 256;
+constexpr int SY_KB = 32, SY_WARPS = 12, SY_THREADS = SY_WARPS * 32, SY_STAGES = 3;
 
-__global__ void __launch_bounds__(SY_THREADS) syrk_kernel(const double* __restrict__ K, const double* __restrict__ dvar,
-                                                          const double* __restrict__ craw, int which, int MP,
-                                                          long long R, int nchunk, double* __restrict__ part,
-                                                          const unsigned int* __restrict__ clamp_count,
-                                                          const double* __restrict__ dmu,
-                                                          double* __restrict__ part_alpha) {
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__host__ __device__ inline size_t syrk_stage_doubles(int MP) { return (size_t)SY_KB * (MP + 4) + 3 * SY_KB; }
+__host__ __device__ inline int syrk_nblocks(int MP) { const int nb = MP / 32; return nb * (nb + 1) / 2; }
+
+__global__ void __launch_bounds__(SY_THREADS, 1)
+syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const double* __restrict__ craw, int which,
+            int MP, long long R, int nchunk, double* __restrict__ part, const unsigned int* __restrict__ clamp_count,
+            const double* __restrict__ dmu, double* __restrict__ part_alpha) {
   if (which == 1 && (clamp_count == nullptr || *clamp_count == 0u)) return;
-  __shared__ double As[SY_K][SY_T + 4];   // As[r][i] (scaled by w_r)
-  __shared__ double Bs[SY_K][SY_T + 4];   // Bs[r][j]
-  const int nb = MP / SY_T + (MP % SY_T ? 1 : 0);
-  // tile index -> (bi >= bj)
-  int tix = blockIdx.x, bi = 0;
-  while (tix > bi) { tix -= bi + 1; ++bi; }
-  const int bj = tix;
-  const int chunk = blockIdx.y;
-  const long long rows_per = ((R + nchunk - 1) / nchunk + SY_K - 1) / SY_K * SY_K;
-  const long long rbeg = (long long)chunk * rows_per, rend = min(R, rbeg + rows_per);
+  extern __shared__ __align__(16) double sy_sh[];
+  const int ld = MP + 4;
+  const size_t stage = syrk_stage_doubles(MP);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wi = warp >> 1, wj = warp & 1;        // warp tile: 16 (i) x 32 (j)
-  double acc[2][4][2];
+  const int nblk = syrk_nblocks(MP);
+  const int group = blockIdx.x, chunk = blockIdx.y;
+  const int q = group * SY_WARPS + warp;
+  const bool active = q < nblk;
+  int bi = 0, bj = 0;
+  if (active) { int rem = q; while (rem > bi) { rem -= bi + 1; ++bi; } bj = rem; }
+  const long long rows_per = ((R + nchunk - 1) / nchunk + SY_KB - 1) / SY_KB * SY_KB;
+  const long long rbeg = (long long)chunk * rows_per;
+  const long long rend = min(R, rbeg + rows_per);
+  const int nst = rend > rbeg ? (int)((rend - rbeg + SY_KB - 1) / SY_KB) : 0;
+  const bool do_alpha = which == 0 && group == 0 && part_alpha != nullptr && dmu != nullptr;
+  const int vec_per_row = MP / 2;
+
+  auto issue = [&](int s) {
+    double* Ts = sy_sh + (size_t)(s % SY_STAGES) * stage;
+    double* ws = Ts + (size_t)SY_KB * ld;
+    const long long r0 = rbeg + (long long)s * SY_KB;
+    for (int idx = tid; idx < SY_KB * vec_per_row; idx += SY_THREADS) {
+      const int r = idx / vec_per_row, c = (idx - r * vec_per_row) * 2;
+      const long long row = r0 + r;
+      const bool ok = row < rend;
+      cp_async16(Ts + (size_t)r * ld + c, ok ? T + (size_t)row * MP + c : T, ok);
+    }
+    if (tid < 3 * SY_KB) {
+      const int arr = tid / SY_KB, k = tid - arr * SY_KB;
+      const long long row = r0 + k;
+      const double* src = arr == 0 ? dvar : (arr == 1 ? dmu : craw);
+      const bool ok = row < rend && src != nullptr;
+      cp_async8(ws + tid, ok ? src + row : (const double*)T, ok);
+    }
+  };
+
+  double acc[4][4][2];
 #pragma unroll
-  for (int x = 0; x < 2; ++x)
+  for (int x = 0; x < 4; ++x)
 #pragma unroll
     for (int y = 0; y < 4; ++y) { acc[x][y][0] = 0.0; acc[x][y][1] = 0.0; }
-  const bool do_alpha = which == 0 && bi == bj && part_alpha != nullptr;   // dalpha_j = sum_r dmu_r K[r][j]
   double al = 0.0;
-  for (long long r0 = rbeg; r0 < rend; r0 += SY_K) {
-    for (int idx = tid; idx < SY_K * SY_T; idx += SY_THREADS) {
-      const int r = idx / SY_T, c = idx - r * SY_T;
-      const long long row = r0 + r;
-      double va = 0.0, vb = 0.0;
-      if (row < rend) {
-        double w = dvar[row];
-        if (which == 1) w = (craw[row] < 0.0) ? w : 0.0;
-        const int ci = bi * SY_T + c, cj = bj * SY_T + c;
-        if (ci < MP) va = w * K[(size_t)row * MP + ci];
-        if (cj < MP) vb = K[(size_t)row * MP + cj];
-        if (do_alpha) al = fma(dmu[row], vb, al);
+
+  for (int s = 0; s < SY_STAGES - 1; ++s) {
+    if (s < nst) issue(s);
+    cp_async_commit();
+  }
+  for (int it = 0; it < nst; ++it) {
+    cp_async_wait<SY_STAGES - 2>();
+    __syncthreads();   // stage `it` has landed for every thread; everyone is done with the buffer refilled below
+    if (it + SY_STAGES - 1 < nst) issue(it + SY_STAGES - 1);
+    cp_async_commit();
+    const double* Ts = sy_sh + (size_t)(it % SY_STAGES) * stage;
+    const double* ws = Ts + (size_t)SY_KB * ld;
+    if (active) {
+      const double* Ap = Ts + 32 * bi + g;
+      const double* Bp = Ts + 32 * bj + g;
+#pragma unroll 2
+      for (int k0 = 0; k0 < SY_KB; k0 += 4) {
+        const int k = k0 + t;
+        double w = ws[k];
+        if (which == 1) w = ws[2 * SY_KB + k] < 0.0 ? w : 0.0;
+        double af[4], bf[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) af[x] = Ap[(size_t)k * ld + 8 * x] * w;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) bf[y] = Bp[(size_t)k * ld + 8 * y];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
       }
-      As[r][c] = va;
-      Bs[r][c] = vb;
     }
-    __syncthreads();
-#pragma unroll
-    for (int k0 = 0; k0 < SY_K; k0 += 4) {
-      double af[2], bf[4];
-#pragma unroll
-      for (int x = 0; x < 2; ++x) af[x] = As[k0 + t][16 * wi + 8 * x + g];
-#pragma unroll
-      for (int y = 0; y < 4; ++y) bf[y] = Bs[k0 + t][32 * wj + 8 * y + g];
-#pragma unroll
-      for (int x = 0; x < 2; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+    if (do_alpha && tid < MP) {
+#pragma unroll 8
+      for (int k = 0; k < SY_KB; ++k) al = fma(ws[SY_KB + k], Ts[(size_t)k * ld + tid], al);
     }
-    __syncthreads();
   }
-  if (do_alpha) {   // tid % 64 is this thread's fixed column; fold the 4 row-phases in a fixed order
-    As[tid / SY_T][tid % SY_T] = al;
-    __syncthreads();
-    if (tid < SY_T && bi * SY_T + tid < MP)
-      part_alpha[(size_t)chunk * MP + bi * SY_T + tid] = (As[0][tid] + As[1][tid]) + (As[2][tid] + As[3][tid]);
+  cp_async_wait<0>();
+  if (active) {
+    double* out = part + ((size_t)chunk * nblk + q) * 1024;
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) out[(8 * x + g) * 32 + 8 * y + 2 * t + e] = acc[x][y][e];
   }
-  double* out = part + ((size_t)chunk * gridDim.x + blockIdx.x) * SY_T * SY_T;
-#pragma unroll
-  for (int x = 0; x < 2; ++x)
-#pragma unroll
-    for (int y = 0; y < 4; ++y)
-#pragma unroll
-      for (int e = 0; e < 2; ++e)
-        out[(size_t)(16 * wi + 8 * x + g) * SY_T + 32 * wj + 8 * y + 2 * t + e] = acc[x][y][e];
-  (void)nb;
+  if (do_alpha && tid < MP) part_alpha[(size_t)chunk * MP + tid] = al;
 }
 
-__global__ void syrk_reduce_kernel(const double* __restrict__ part, int ntiles, int nchunk, int MP,
-                                   double* __restrict__ A, int which, const unsigned int* __restrict__ clamp_count,
+__global__ void syrk_reduce_kernel(const double* __restrict__ part, int nchunk, int MP, double* __restrict__ A,
+                                   int which, const unsigned int* __restrict__ clamp_count,
                                    double* __restrict__ clamp_flag_out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx == 0 && which == 1 && clamp_flag_out) *clamp_flag_out = clamp_count ? (double)(*clamp_count) : 0.0;
   if (idx >= MP * MP) return;
   if (which == 1 && (clamp_count == nullptr || *clamp_count == 0u)) { A[idx] = 0.0; return; }
   int i = idx / MP, j = idx - (idx / MP) * MP;
-  if (j > i) { const int tmp = i; i = j; j = tmp; }
-  const int bi = i / SY_T, bj = j / SY_T;
-  const int tile = bi * (bi + 1) / 2 + bj;
-  const int li = i - bi * SY_T, lj = j - bj * SY_T;
+  if (j > i) { const int tmp = i; i = j; j = tmp; }      // lower triangle (also inside diagonal blocks) -> symmetric
+  const int bi = i >> 5, bj = j >> 5;
+  const int q = bi * (bi + 1) / 2 + bj;
+  const int nblk = syrk_nblocks(MP);
+  const size_t off = (size_t)q * 1024 + (size_t)(i & 31) * 32 + (j & 31);
   double s = 0.0;
-  for (int c = 0; c < nchunk; ++c) s += part[((size_t)c * ntiles + tile) * SY_T * SY_T + (size_t)li * SY_T + lj];
+  for (int c = 0; c < nchunk; ++c) s += part[(size_t)c * nblk * 1024 + off];
   A[idx] = s;
 }
 
@@ -695,7 +884,8 @@ static int num_sms() {
 
 int row_grid(long long R) {
   const long long ntiles = (R + TR - 1) / TR;
-  return (int)(ntiles < (long long)num_sms() ? (ntiles > 0 ? ntiles : 1) : num_sms());
+  const long long cap = (long long)num_sms() * ROW_CTAS_PER_SM;
+  return (int)(ntiles < cap ? (ntiles > 0 ? ntiles : 1) : cap);
 }
 
 int launch_row_fwd(const RowArgs& a, cudaStream_t st) {
@@ -739,31 +929,34 @@ int launch_reduce_partials(const double* part, int nblocks, int n, int stride, d
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-int syrk_ntiles(int MP) {
-  const int nb = (MP + SY_T - 1) / SY_T;
-  return nb * (nb + 1) / 2;
-}
+int syrk_ngroups(int MP) { return (syrk_nblocks(MP) + SY_WARPS - 1) / SY_WARPS; }
 
 int syrk_nchunk(int MP, long long R) {
-  const int nt = syrk_ntiles(MP);
-  long long want = (2LL * num_sms() + nt - 1) / nt;
-  const long long maxc = (R + 4 * SY_K - 1) / (4 * SY_K);
+  long long want = num_sms() / syrk_ngroups(MP);           // one CTA per SM (the pipeline takes most of its smem)
+  const long long maxc = (R + 2 * SY_KB - 1) / (2 * SY_KB);
   if (want > maxc) want = maxc;
   if (want < 1) want = 1;
   return (int)want;
 }
 
-size_t syrk_part_doubles(int MP, long long R) { return (size_t)syrk_ntiles(MP) * syrk_nchunk(MP, R) * SY_T * SY_T; }
+size_t syrk_part_doubles(int MP, long long R) { return (size_t)syrk_nblocks(MP) * syrk_nchunk(MP, R) * 1024; }
 
 // part: syrk_part_doubles(MP, R) doubles of scratch; part_alpha: nchunk * MP doubles (which == 0 only)
 int launch_syrk(const double* K, const double* dvar, const double* craw, int which, int MP, long long R,
                 double* part, double* A, const unsigned int* clamp_count, const double* dmu, double* part_alpha,
                 double* dalpha, double* clamp_flag_out, cudaStream_t st) {
-  const int nt = syrk_ntiles(MP), nc = syrk_nchunk(MP, R);
-  dim3 grid(nt, nc);
-  MOBO_LAUNCH("syrk_kernel", st, syrk_kernel<<<grid, SY_THREADS, 0, st>>>(K, dvar, craw, which, MP, R, nc, part, clamp_count, dmu,
-                                           which == 0 ? part_alpha : nullptr));
-  MOBO_LAUNCH("syrk_reduce_kernel", st, syrk_reduce_kernel<<<(MP * MP + 255) / 256, 256, 0, st>>>(part, nt, nc, MP, A, which, clamp_count, clamp_flag_out));
+  const int nc = syrk_nchunk(MP, R);
+  const size_t smem = SY_STAGES * syrk_stage_doubles(MP) * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(SY_STAGES * syrk_stage_doubles(MAX_MP) * sizeof(double)));
+    attr_done = true;
+  }
+  dim3 grid(syrk_ngroups(MP), nc);
+  MOBO_LAUNCH("syrk_kernel", st, syrk_kernel<<<grid, SY_THREADS, smem, st>>>(K, dvar, craw, which, MP, R, nc, part, clamp_count,
+                                           which == 0 ? dmu : nullptr, which == 0 ? part_alpha : nullptr));
+  MOBO_LAUNCH("syrk_reduce_kernel", st, syrk_reduce_kernel<<<(MP * MP + 255) / 256, 256, 0, st>>>(part, nc, MP, A, which, clamp_count, clamp_flag_out));
   if (which == 0 && part_alpha && dalpha)
     MOBO_LAUNCH("reduce_partials_kernel", st, reduce_partials_kernel<<<(MP + 127) / 128, 128, 0, st>>>(part_alpha, nc, MP, MP, dalpha, 0));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
