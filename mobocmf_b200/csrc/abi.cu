@@ -3,6 +3,7 @@
 #include <string.h>
 #include "../../include/mobocmf_b200.h"
 #include "matrix_ops.cu"
+#include "opchain.cu"
 #include "row_pass.cu"
 #include "step.cu"
 
@@ -97,32 +98,15 @@ int mobo_model_precompute(int nl, const int* kinds, int d, int M, const double* 
   LayerBatch b;
   MOBO_TRY(fill_batch(b, nl, kinds, d, M, Zx, zf, theta, m, Lq, ops));
   const int MP = b.MP;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_done = true;
-  }
-  const dim3 ew_grid((MP * MP + 255) / 256, nl);
-  MOBO_LAUNCH("kzz_kernel", st, kzz_kernel<<<ew_grid, 256, 0, st>>>(b, jitter, OPS_P, 1));
-  const size_t chol_smem = (size_t)(64 * CH_LD + (size_t)MP * CH_LD) * sizeof(double);
-  MOBO_LAUNCH("chol_inv_kernel", st, chol_inv_kernel<<<nl, CH_THREADS, chol_smem, st>>>(b));
-  MOBO_LAUNCH("padtril_kernel", st, padtril_kernel<<<ew_grid, 256, 0, st>>>(b));
-  GemmOperand A, B;
-  double* C[MAX_BATCH]; double* Ct[MAX_BATCH];
-  FinBatch f;
-  for (int i = 0; i < MAX_BATCH; ++i) {
-    const bool ok = i < nl;
-    A.p[i] = ok ? ops[i] + ops_block(MP, OPS_W) : nullptr;
-    B.p[i] = ok ? ops[i] + ops_block(MP, OPS_LQ) : nullptr;
-    C[i] = ok ? ops[i] + ops_block(MP, OPS_H) : nullptr;
-    Ct[i] = ok ? ops[i] + ops_block(MP, OPS_HT) : nullptr;
-    f.rowstat[i] = ok ? ops[i] + ops_rowstat(MP) : nullptr;
-    f.counter[i] = ok ? reinterpret_cast<unsigned int*>(ops[i] + ops_scal(MP) + SC_COUNTER) : nullptr;
-  }
-  A.trans = false; A.tri = 1; B.trans = false; B.tri = 1;
-  MOBO_TRY(gemm_batched(nl, MP, A, B, C, Ct, 1.0, 0.0, nullptr, st));
-  MOBO_LAUNCH("finalize_kernel", st,
-              finalize_kernel<<<dim3((MP + FIN_WARPS - 1) / FIN_WARPS, nl), FIN_WARPS * 32, 0, st>>>(b, f));
+  // one cooperative launch: a CTA per 32 x 32 block of the lower triangle of every layer (opchain.cu)
+  const int nb = MP / 32, nblk = nb * (nb + 1) / 2;
+  MOBO_LAUNCH("opchain_reset_kernel", st, opchain_reset_kernel<<<nl, 128, 0, st>>>(b));
+  void* args[] = {(void*)&b, (void*)&jitter};
+  prof_begin("opchain_kernel", st);
+  const cudaError_t e = cudaLaunchCooperativeKernel((const void*)opchain_kernel, dim3(nl * nblk), dim3(OC_THREADS), args,
+                                                    0, st);
+  prof_end(st);
+  if (e != cudaSuccess) return -1;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

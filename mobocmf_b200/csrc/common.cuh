@@ -41,7 +41,8 @@ constexpr int kMaxD = 8;               // max number of x columns (ARD dims) han
 constexpr double kMinVariance = 1e-10; // gpytorch settings.min_variance (fp64), quirk Q9
 
 // ---- operator buffer layout (doubles), one per (model, layer); MP = M rounded up to a multiple of 32 ----
-// [L | W | WT | H | HT | P | LQ]  seven MP x MP row-major blocks, then beta[MP], alpha[MP], scal[16], rowstat[4 MP]
+// [L | W | WT | H | HT | P | LQ]  seven MP x MP row-major blocks, then beta[MP], alpha[MP], scal[16], rowstat[4 MP],
+// flags[128]
 //   L = chol(K_zz + jitter I), W = L^-1, WT = W^T, H = W tril(L_q), HT = H^T, P = K_zz + jitter I, LQ = tril(L_q)
 // The GRADIENT buffer of an operator buffer has the same layout and carries, by convention of this library,
 //   block OPS_W: A2 = sum_r dvar_r t_r t_r^T (t = W k),  block OPS_H: Ac = same over clamped rows only,
@@ -55,7 +56,9 @@ __host__ __device__ inline size_t ops_beta(int MP) { return (size_t)OPS_NBLOCKS 
 __host__ __device__ inline size_t ops_alpha(int MP) { return (size_t)OPS_NBLOCKS * MP * MP + MP; }
 __host__ __device__ inline size_t ops_scal(int MP) { return (size_t)OPS_NBLOCKS * MP * MP + 2 * MP; }
 __host__ __device__ inline size_t ops_rowstat(int MP) { return (size_t)OPS_NBLOCKS * MP * MP + 2 * MP + 16; }
-__host__ __device__ inline size_t ops_size(int MP) { return (size_t)OPS_NBLOCKS * MP * MP + 6 * MP + 16; }
+// 256 ints of block-to-block flags of the cooperative operator-chain kernel (opchain.cu)
+__host__ __device__ inline size_t ops_flags(int MP) { return (size_t)OPS_NBLOCKS * MP * MP + 6 * MP + 16; }
+__host__ __device__ inline size_t ops_size(int MP) { return (size_t)OPS_NBLOCKS * MP * MP + 6 * MP + 16 + 128; }
 
 // D(8x8) += A(8x4, row) * B(4x8, col).  lane = 4*g + t:  A[g][t], B[t][g], C[g][2t..2t+1].
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {

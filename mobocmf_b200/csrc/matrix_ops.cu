@@ -210,229 +210,27 @@ __global__ void reduce_batch_kernel(ReduceBatch r, int nblocks, int stride) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// L = chol(P) and W = L^-1 (also W^T) in one CTA per matrix; operands stay in L2, panels in shared memory.
-// Blocked right-looking Cholesky (NB = 32): the diagonal block is factorised and inverted in registers by one warp
-// (lane = row, columns exchanged by shuffles), the panel is A D^-T and the trailing update is a DMMA SYRK.  The
-// inverse reuses the inverted diagonal blocks and fills the block diagonals in order of increasing distance:
-// W_ik = -W_ii (sum_{j=k}^{i-1} L_ij W_jk).
+// 32 x 32 Cholesky factor in registers of one warp (lane = row, columns exchanged by shuffles); used by the
+// diagonal CTAs of the operator-chain kernel (opchain.cu).
 // ---------------------------------------------------------------------------------------------------
-constexpr int CH_NB = 32, CH_THREADS = 512, CH_WARPS = CH_THREADS / 32, CH_LD = 36;
 
-__device__ __forceinline__ void chol32_inwarp(double (&row)[32], int lane, int& fail) {
-  // row[c] = A[lane][c] (lower part valid).  On exit row[c] = L[lane][c] for c <= lane.
+__device__ __forceinline__ void chol32_inwarp(double (&row)[32], double& rinv, int lane, int& fail) {
+  // row[c] = A[lane][c] (lower part valid).  On exit row[c] = L[lane][c] for c <= lane and rinv = 1 / L[lane][lane].
+  // Right-looking; the pivot's reciprocal square root (1 ulp) replaces the square root and the division of the
+  // textbook form, which sit on the critical path of the whole operator chain.
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const double djj = __shfl_sync(0xffffffffu, row[j], j);
     if (!(djj > 0.0)) fail = 1;
-    const double ljj = sqrt(djj);
-    if (lane == j) row[j] = ljj;
-    else if (lane > j) row[j] = row[j] / ljj;
+    const double r = rsqrt(djj);
+    if (lane == j) { row[j] = djj * r; rinv = r; }
+    else if (lane > j) row[j] = row[j] * r;
 #pragma unroll
     for (int c = j + 1; c < 32; ++c) {
       const double lcj = __shfl_sync(0xffffffffu, row[j], c);   // L[c][j]
       if (lane >= c) row[c] = fma(-row[j], lcj, row[c]);
     }
   }
-}
-
-__global__ void __launch_bounds__(CH_THREADS, 1) chol_inv_kernel(LayerBatch b) {
-  extern __shared__ __align__(16) double sh[];
-  const int MP = b.MP;
-  double* ops = b.ops[blockIdx.x];
-  const double* P = ops + ops_block(MP, OPS_P);
-  double* L = ops + ops_block(MP, OPS_L);
-  double* W = ops + ops_block(MP, OPS_W);
-  double* WT = ops + ops_block(MP, OPS_WT);
-  double* D = sh;                         // [32][CH_LD]   factor of the current diagonal block
-  double* Dinv = sh + 32 * CH_LD;         // [32][CH_LD]   its inverse
-  double* panel = sh + 64 * CH_LD;        // [(MP-32)][CH_LD]  (also S scratch of the inverse phases)
-  __shared__ int fail_flag;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int nb = MP / CH_NB;
-  if (tid == 0) fail_flag = 0;
-  for (int idx = tid; idx < MP * MP; idx += CH_THREADS) {
-    const int i = idx / MP, j = idx - i * MP;
-    L[idx] = j <= i ? P[idx] : 0.0;
-    W[idx] = 0.0;
-  }
-  __syncthreads();
-  for (int kb = 0; kb < nb; ++kb) {
-    const int k0 = kb * CH_NB;
-    if (warp == 0) {
-      double row[32];
-      const double* src = L + (size_t)(k0 + lane) * MP + k0;
-#pragma unroll
-      for (int c = 0; c < 32; ++c) row[c] = src[c];
-      int fail = 0;
-      chol32_inwarp(row, lane, fail);
-      if (fail) fail_flag = 1;
-      double* dst = L + (size_t)(k0 + lane) * MP + k0;
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const double v = c <= lane ? row[c] : 0.0;
-        dst[c] = v;
-        D[lane * CH_LD + c] = v;
-      }
-      __syncwarp();
-      // inverse of the lower-triangular block: lane = column c, forward substitution down the rows
-      double x[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        double s = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < i; ++k) s = fma(-D[i * CH_LD + k], x[k], s);
-        x[i] = (i >= lane) ? s / D[i * CH_LD + i] : 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        Dinv[i * CH_LD + lane] = x[i];
-        W[(size_t)(k0 + i) * MP + k0 + lane] = x[i];
-      }
-    }
-    __syncthreads();
-    const int nrows = MP - k0 - CH_NB;
-    if (nrows > 0) {
-      // panel X = A Dinv^T : warp items of 16 rows x 32 cols
-      for (int item = warp; item < nrows / 16; item += CH_WARPS) {
-        const int r0 = item * 16;
-        double acc[2][4][2];
-#pragma unroll
-        for (int x = 0; x < 2; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y) { acc[x][y][0] = 0.0; acc[x][y][1] = 0.0; }
-        const double* Arow = L + (size_t)(k0 + CH_NB + r0) * MP + k0;
-#pragma unroll
-        for (int kk = 0; kk < CH_NB; kk += 4) {
-          double af[2], bf[4];
-#pragma unroll
-          for (int x = 0; x < 2; ++x) af[x] = Arow[(size_t)(8 * x + g) * MP + kk + t];
-#pragma unroll
-          for (int y = 0; y < 4; ++y) bf[y] = Dinv[(8 * y + g) * CH_LD + kk + t];   // B[k][n] = Dinv[n][k]
-#pragma unroll
-          for (int x = 0; x < 2; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int x = 0; x < 2; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int rr = r0 + 8 * x + g, cc = 8 * y + 2 * t + e;
-              panel[(size_t)rr * CH_LD + cc] = acc[x][y][e];
-              L[(size_t)(k0 + CH_NB + rr) * MP + k0 + cc] = acc[x][y][e];
-            }
-      }
-      __syncthreads();
-      // trailing update: L[i][j] -= panel[i] . panel[j]  on 32x32 blocks (bi >= bj)
-      const int nblk = nrows / CH_NB, nb2 = nblk * (nblk + 1) / 2;
-      for (int blk = warp; blk < nb2; blk += CH_WARPS) {
-        int bi = 0, rem = blk;
-        while (rem > bi) { rem -= bi + 1; ++bi; }
-        const int bj = rem;
-        double acc[4][4][2];
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y) { acc[x][y][0] = 0.0; acc[x][y][1] = 0.0; }
-#pragma unroll
-        for (int kk = 0; kk < CH_NB; kk += 4) {
-          double af[4], bf[4];
-#pragma unroll
-          for (int x = 0; x < 4; ++x) af[x] = panel[(size_t)(bi * CH_NB + 8 * x + g) * CH_LD + kk + t];
-#pragma unroll
-          for (int y = 0; y < 4; ++y) bf[y] = panel[(size_t)(bj * CH_NB + 8 * y + g) * CH_LD + kk + t];
-#pragma unroll
-          for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
-        }
-        double* base = L + (size_t)(k0 + CH_NB + bi * CH_NB) * MP + k0 + CH_NB + bj * CH_NB;
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int ii = 8 * x + g, jj = 8 * y + 2 * t + e;
-              if (bi > bj || jj <= ii) base[(size_t)ii * MP + jj] -= acc[x][y][e];
-            }
-      }
-    }
-    __syncthreads();
-  }
-  // ---- W = L^-1: block diagonals of increasing distance; 4 warps per 32x32 block (16x16 quadrants) ----
-  double* Sblk = panel;                    // [nb][32][CH_LD]
-  for (int dd = 1; dd < nb; ++dd) {
-    const int nblocks = nb - dd;
-    for (int item = warp; item < nblocks * 4; item += CH_WARPS) {
-      const int bq = item >> 2, q = item & 3;
-      const int k = bq, i = bq + dd;
-      const int r0 = 16 * (q >> 1), c0 = 16 * (q & 1);
-      double acc[2][2][2] = {};
-      for (int j = k; j < i; ++j) {
-        const double* Lij = L + (size_t)(32 * i) * MP + 32 * j;
-        const double* Wjk = W + (size_t)(32 * j) * MP + 32 * k;
-#pragma unroll
-        for (int kk = 0; kk < 32; kk += 4) {
-          double af[2], bf[2];
-#pragma unroll
-          for (int x = 0; x < 2; ++x) af[x] = Lij[(size_t)(r0 + 8 * x + g) * MP + kk + t];
-#pragma unroll
-          for (int y = 0; y < 2; ++y) bf[y] = Wjk[(size_t)(kk + t) * MP + c0 + 8 * y + g];
-#pragma unroll
-          for (int x = 0; x < 2; ++x)
-#pragma unroll
-            for (int y = 0; y < 2; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
-        }
-      }
-      double* S = Sblk + (size_t)bq * 32 * CH_LD;
-#pragma unroll
-      for (int x = 0; x < 2; ++x)
-#pragma unroll
-        for (int y = 0; y < 2; ++y)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) S[(size_t)(r0 + 8 * x + g) * CH_LD + c0 + 8 * y + 2 * t + e] = acc[x][y][e];
-    }
-    __syncthreads();
-    for (int item = warp; item < nblocks * 4; item += CH_WARPS) {
-      const int bq = item >> 2, q = item & 3;
-      const int k = bq, i = bq + dd;
-      const int r0 = 16 * (q >> 1), c0 = 16 * (q & 1);
-      const double* Wii = W + (size_t)(32 * i) * MP + 32 * i;
-      const double* S = Sblk + (size_t)bq * 32 * CH_LD;
-      double acc[2][2][2] = {};
-#pragma unroll
-      for (int kk = 0; kk < 32; kk += 4) {
-        double af[2], bf[2];
-#pragma unroll
-        for (int x = 0; x < 2; ++x) af[x] = Wii[(size_t)(r0 + 8 * x + g) * MP + kk + t];
-#pragma unroll
-        for (int y = 0; y < 2; ++y) bf[y] = S[(size_t)(kk + t) * CH_LD + c0 + 8 * y + g];
-#pragma unroll
-        for (int x = 0; x < 2; ++x)
-#pragma unroll
-          for (int y = 0; y < 2; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
-      }
-      double* Wik = W + (size_t)(32 * i) * MP + 32 * k;
-#pragma unroll
-      for (int x = 0; x < 2; ++x)
-#pragma unroll
-        for (int y = 0; y < 2; ++y)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) Wik[(size_t)(r0 + 8 * x + g) * MP + c0 + 8 * y + 2 * t + e] = -acc[x][y][e];
-    }
-    __threadfence_block();
-    __syncthreads();
-  }
-  for (int idx = tid; idx < MP * MP; idx += CH_THREADS) {
-    const int i = idx / MP, j = idx - i * MP;
-    WT[idx] = W[(size_t)j * MP + i];
-  }
-  if (tid == 0) (ops + ops_scal(MP))[SC_STATUS] = fail_flag ? 1.0 : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -557,69 +355,6 @@ static int gemm_batched(int nbatch, int n, const GemmOperand& A, const GemmOpera
   dim3 grid(n / GM_T, n / GM_T, nbatch);
   MOBO_LAUNCH("gemm_kernel", st, gemm_kernel<<<grid, GM_THREADS, 0, st>>>(a));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
-}
-
-// LQ = tril(Lq) zero padded to MP
-__global__ void padtril_kernel(LayerBatch b) {
-  const int bi = blockIdx.y, M = b.M, MP = b.MP;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= MP * MP) return;
-  const int i = idx / MP, j = idx - i * MP;
-  (b.ops[bi] + ops_block(MP, OPS_LQ))[idx] = (i < M && j <= i) ? b.Lq[bi][(size_t)i * M + j] : 0.0;
-}
-
-// beta = W m and the KL pieces; warp per row, the last CTA of each matrix folds the row statistics in row order.
-constexpr int FIN_WARPS = 8;
-struct FinBatch { double* rowstat[MAX_BATCH]; unsigned int* counter[MAX_BATCH]; };
-__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(LayerBatch b, FinBatch f) {
-  const int bi = blockIdx.y, M = b.M, MP = b.MP;
-  double* ops = b.ops[bi];
-  const double* L = ops + ops_block(MP, OPS_L);
-  const double* W = ops + ops_block(MP, OPS_W);
-  const double* H = ops + ops_block(MP, OPS_H);
-  const double* LQ = ops + ops_block(MP, OPS_LQ);
-  const double* m = b.m[bi];
-  double* beta = ops + ops_beta(MP);
-  double* rowstat = f.rowstat[bi];       // [4][MP]: beta^2, |H_i|^2, 2 log L_ii, log Lq_ii^2
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * FIN_WARPS + warp;
-  if (i < MP) {
-    double s = 0.0, h = 0.0;
-    if (i < M)
-      for (int k = lane; k <= i; k += 32) s = fma(W[(size_t)i * MP + k], m[k], s);
-    for (int k = lane; k <= i; k += 32) { const double v = H[(size_t)i * MP + k]; h = fma(v, v, h); }
-    s = warp_sum(s);
-    h = warp_sum(h);
-    if (lane == 0) {
-      beta[i] = s;
-      rowstat[i] = s * s;
-      rowstat[MP + i] = h;
-      const double q = i < M ? LQ[(size_t)i * MP + i] : 1.0;
-      rowstat[2 * MP + i] = i < M ? 2.0 * log(L[(size_t)i * MP + i]) : 0.0;
-      rowstat[3 * MP + i] = log(q * q);
-    }
-  }
-  __shared__ bool last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(f.counter[bi], 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (last && warp == 0) {
-    __threadfence();
-    double v[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      double s = 0.0;
-      for (int r = lane; r < MP; r += 32) s += ((volatile double*)rowstat)[q * MP + r];
-      v[q] = warp_sum(s);
-    }
-    if (lane == 0) {
-      double* scal = ops + ops_scal(MP);
-      scal[SC_BETA2] = v[0]; scal[SC_H2] = v[1]; scal[SC_LOGDET_P] = v[2]; scal[SC_LOGDET_Q] = v[3];
-      scal[SC_KL] = 0.5 * (v[2] - v[3] + v[0] + v[1] - (double)M);
-      *f.counter[bi] = 0u;
-    }
-  }
 }
 
 // dm = W^T (b + g beta).  Warp per row of W^T.

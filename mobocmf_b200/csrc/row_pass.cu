@@ -72,6 +72,7 @@ struct KernFast {
   double la1, laf, la2, vlin, cf, ilf;
   double a1, af, a2, lf;
   double c1[kMaxD], c2[kMaxD];     // -0.5 log2(e) / l^2
+  double2 cc[kMaxD];               // (c1, c2) interleaved: one 16-byte broadcast load per dimension
   double il1[kMaxD], il2[kMaxD];   // 1 / l^2
 };
 
@@ -242,6 +243,7 @@ __device__ inline void load_kern_fast(KernFast& kf, int kind, int d, const doubl
       kf.c1[c] = nhl2e * kf.il1[c]; kf.c2[c] = nhl2e * kf.il2[c];
     }
   }
+  for (int c = 0; c < kMaxD; ++c) kf.cc[c] = make_double2(kf.c1[c], kf.c2[c]);
 }
 
 __device__ __forceinline__ void load_inducing(const RowArgs& a, RowSmem& sm) {
@@ -448,11 +450,8 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, RowSmem& sm, const 
   const double* tab = sm.e2tab;
   const int M = a.M, nch = a.MP / 32;
   const int rbase = warp * RPW;
-  double f[RPW], vf[RPW], c1[D], c2[D];
-#pragma unroll
-  for (int i = 0; i < RPW; ++i) { f[i] = sm.fs[rbase + i]; vf[i] = kf.vlin * f[i]; }
-#pragma unroll
-  for (int c = 0; c < D; ++c) { c1[c] = kf.c1[c]; c2[c] = kf.c2[c]; }
+  // register budget: the accumulators below stay in registers for the whole tile, so the per-dimension coefficients
+  // and the rows' coordinates are re-read from shared memory (broadcast loads) instead of being cached
   const double la1 = kf.la1, la2 = kf.la2, laf = kf.laf, cf = kf.cf, vlin = kf.vlin, ilf = kf.ilf;
   double th[5], tl1[D], tl2[D], rdf[RPW], rdx[XGRAD ? RPW : 1][D];
 #pragma unroll
@@ -474,16 +473,18 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, RowSmem& sm, const 
     const double zf = sm.zfs[j], vz = vlin * zf;
     const bool jok = j < M;
     double azf = 0.0;
-#pragma unroll
+#pragma unroll 2
     for (int i = 0; i < RPW; ++i) {
       const double gk = jok ? Ks[(size_t)(rbase + i) * ldb + j] : 0.0;
+      const double fi = sm.fs[rbase + i];
       double diff[D], d2[D], D1 = la1, D2 = la2;
 #pragma unroll
       for (int c = 0; c < D; ++c) {
+        const double2 cc = kf.cc[c];
         diff[c] = sm.xs[rbase + i][c] - z[c];
         d2[c] = diff[c] * diff[c];
-        D1 = fma(d2[c], c1[c], D1);
-        if (KIND == 1) D2 = fma(d2[c], c2[c], D2);
+        D1 = fma(d2[c], cc.x, D1);
+        if (KIND == 1) D2 = fma(d2[c], cc.y, D2);
       }
       if (KIND == 0) {
         const double g1 = gk * exp2_tab(D1, tab);
@@ -497,17 +498,17 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, RowSmem& sm, const 
           for (int c = 0; c < D; ++c) rdx[i][c] = fma(-g1 * diff[c], kf.il1[c], rdx[i][c]);
         }
       } else {
-        const double dff = f[i] - zf, dff2 = dff * dff;
+        const double dff = fi - zf, dff2 = dff * dff;
         const double Efp = exp2_tab(fma(dff2, cf, laf), tab);        // af Ef
         const double s1 = exp2_tab(D1, tab), s2 = exp2_tab(D2, tab);  // a1 E1, a2 E2
-        const double fz = f[i] * zf;
+        const double fz = fi * zf;
         const double gg = fma(vlin, fz, Efp);                         // k_lin + k_f
         const double gs1 = gk * s1, g2 = gk * s2;
         const double g1 = gs1 * gg, gEf = gs1 * Efp;
         const double q = gEf * (dff * ilf);                           // gk a1 E1 af Ef (f - f') / lf^2
         rdf[i] += fma(gs1, vz, -q);
         if (PARAM) {
-          azf += fma(gs1, vf[i], q);
+          azf += fma(gs1, vlin * fi, q);
           th[0] += g1;
           th[1] = fma(gs1, fz, th[1]);
           th[2] += gEf;
@@ -530,9 +531,10 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, RowSmem& sm, const 
     const int r = rbase + i;
     const bool rok = r < nvalid;
     const double dvm = sm.dvar[r] * sm.mask[r];
+    const double fi = sm.fs[r];
     if (KIND == 1) {
       const double sdf = warp_sum(rdf[i]);
-      if (lane == 0 && rok) a.df[row0 + r] = sdf + dvm * 2.0 * kf.a1 * vlin * f[i];
+      if (lane == 0 && rok) a.df[row0 + r] = sdf + dvm * 2.0 * kf.a1 * vlin * fi;
     }
     if (XGRAD) {
 #pragma unroll
@@ -545,8 +547,8 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, RowSmem& sm, const 
       if (KIND == 0) {
         th[0] += dvm * kf.a1;
       } else {
-        th[0] += dvm * kf.a1 * fma(vlin * f[i], f[i], kf.af);
-        th[1] += dvm * kf.a1 * f[i] * f[i];
+        th[0] += dvm * kf.a1 * fma(vlin * fi, fi, kf.af);
+        th[1] += dvm * kf.a1 * fi * fi;
         th[2] += dvm * kf.a1 * kf.af;
         th[4] += dvm * kf.a2;
       }
@@ -715,14 +717,16 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_bwd_kernel(c
   }
 }
 
-// sums the per-CTA partials in a fixed order: out[i] = sum_b part[b][i]
+// sums the per-CTA partials in a fixed order: out[i] = sum_b part[b][i].  One warp per output element: lanes stride
+// over the partials, then a butterfly (the order depends only on nblocks -> deterministic).
 __global__ void reduce_partials_kernel(const double* __restrict__ part, int nblocks, int n, int stride,
                                        double* __restrict__ out, int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n) return;
   double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += part[(size_t)b * stride + i];
-  out[i] = accumulate ? out[i] + s : s;
+  for (int b = lane; b < nblocks; b += 32) s += part[(size_t)b * stride + i];
+  s = warp_sum(s);
+  if (lane == 0) out[i] = accumulate ? out[i] + s : s;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -925,7 +929,7 @@ int launch_row_bwd(const RowArgs& a, int grid, cudaStream_t st) {
 
 int launch_reduce_partials(const double* part, int nblocks, int n, int stride, double* out, int accumulate,
                            cudaStream_t st) {
-  MOBO_LAUNCH("reduce_partials_kernel", st, reduce_partials_kernel<<<(n + 127) / 128, 128, 0, st>>>(part, nblocks, n, stride, out, accumulate));
+  MOBO_LAUNCH("reduce_partials_kernel", st, reduce_partials_kernel<<<(n + 3) / 4, 128, 0, st>>>(part, nblocks, n, stride, out, accumulate));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -958,7 +962,7 @@ int launch_syrk(const double* K, const double* dvar, const double* craw, int whi
                                            which == 0 ? dmu : nullptr, which == 0 ? part_alpha : nullptr));
   MOBO_LAUNCH("syrk_reduce_kernel", st, syrk_reduce_kernel<<<(MP * MP + 255) / 256, 256, 0, st>>>(part, nc, MP, A, which, clamp_count, clamp_flag_out));
   if (which == 0 && part_alpha && dalpha)
-    MOBO_LAUNCH("reduce_partials_kernel", st, reduce_partials_kernel<<<(MP + 127) / 128, 128, 0, st>>>(part_alpha, nc, MP, MP, dalpha, 0));
+    MOBO_LAUNCH("reduce_partials_kernel", st, reduce_partials_kernel<<<(MP + 3) / 4, 128, 0, st>>>(part_alpha, nc, MP, MP, dalpha, 0));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
