@@ -52,7 +52,8 @@ size_t mobo_rows_save_doubles(int M, long long R) {
 
 size_t mobo_rows_bwd_work_doubles(int M, long long R) {
   const int MP = padded(M);
-  return (size_t)256 * ROW_CTAS_PER_SM * (MAX_THETA + MP) + syrk_part_doubles(MP, R) + (size_t)syrk_nchunk(MP, R) * MP + 64;
+  return (size_t)256 * KG_CTAS_PER_SM * (MAX_THETA + MP) + syrk_part_doubles(MP, R) + (size_t)syrk_nchunk(MP, R) * MP + 64 +
+         mobo_rows_save_doubles(M, R);   // + the dk scratch [R][MP]
 }
 
 size_t mobo_precompute_bwd_work_doubles(int M) {
@@ -238,7 +239,7 @@ static void fill_row_args(RowArgs& a, int kind, int d, int M, const double* Zx, 
   a.eps = eps; a.eps_mod = eps_mod < 1 ? 1 : eps_mod; a.f_direct = f_direct; a.R = R; a.training = training;
   a.mu = nullptr; a.var = nullptr; a.craw = nullptr; a.clamp_count = nullptr;
   a.Tsave = nullptr; a.Usave = nullptr;
-  a.dmu = nullptr; a.dvar = nullptr; a.df = nullptr; a.dxrow = nullptr; a.part_theta = nullptr; a.part_zf = nullptr;
+  a.dmu = nullptr; a.dvar = nullptr; a.dk = nullptr; a.df = nullptr; a.dxrow = nullptr; a.part_theta = nullptr; a.part_zf = nullptr;
   a.want_param_grads = 0; a.want_x_grads = 0;
 }
 
@@ -272,13 +273,14 @@ int mobo_layer_rows_bwd(int kind, int d, int M, const double* Zx, const double* 
   a.df = df; a.dxrow = dxrow;
   a.want_param_grads = want_param_grads; a.want_x_grads = dxrow != nullptr;
   if (!a.want_param_grads && !a.want_x_grads) a.want_param_grads = 1;
-  const int grid = row_grid(R);
-  double* part_theta = work;
+  const int grid = kgrad_grid(R);
+  a.dk = work;                                                   // [R][MP] scratch, first so that it stays aligned
+  double* part_theta = work + mobo_rows_save_doubles(M, R);
   double* part_zf = part_theta + (size_t)grid * MAX_THETA;
   double* part_syrk = part_zf + (size_t)grid * MP;
   double* part_alpha = part_syrk + syrk_part_doubles(MP, R);
   a.part_theta = part_theta; a.part_zf = part_zf;
-  MOBO_TRY(launch_row_bwd(a, grid, st));
+  MOBO_TRY(launch_row_bwd(a, st));
   if (a.want_param_grads && dtheta) {
     MOBO_TRY(launch_reduce_partials(part_theta, grid, theta_size(kind, d), MAX_THETA, dtheta, 0, st));
     if (kind == 1 && dzf) MOBO_TRY(launch_reduce_partials(part_zf, grid, M, MP, dzf, 0, st));

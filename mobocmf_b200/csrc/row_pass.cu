@@ -55,6 +55,7 @@ struct RowArgs {
   // backward inputs / outputs
   const double* dmu;
   const double* dvar;
+  double* dk;              // scratch [R][MP]: d loss / d K(z_j, row r), written by the product kernel, read by kgrad
   double* df;              // R: d loss / d f_r   (kind 1)
   double* dxrow;           // optional R x d: d loss / d x of each row
   double* part_theta;      // [grid][MAX_THETA]
@@ -98,19 +99,28 @@ __device__ __forceinline__ double exp2_tab(double y, const double* __restrict__ 
   return __hiloint2double(__double2hiint(res) + ((n >> kExp2TabBits) << 20), __double2loint(res));
 }
 
-struct RowSmem {
+constexpr int RPW = 4;   // tile rows per warp in the covariance phases (independent exponent chains per thread)
+
+// Shared state of the covariance phases for NW warps (NW * RPW rows per tile).  BWD adds the per-warp accumulators.
+template <int NW, bool BWD>
+struct CovSmem {
+  static constexpr int WARPS = NW, ROWS = NW * RPW, THREADS = NW * 32;
   KernFast kf;
   double e2tab[kExp2Tab];
-  double red[3][NCH_MAX][TR];     // per warp-pair partial column sums: q1, mu, q2
-  double xs[TR][kMaxD];
-  double fs[TR];
-  double kxx[TR];
-  double dmu[TR], dvar[TR], mask[TR];
+  double xs[ROWS][kMaxD];
+  double fs[ROWS];
+  double kxx[ROWS];
+  double dvar[ROWS], mask[ROWS];
   double zsT[kMaxD][MAX_MP];
   double zfs[MAX_MP];
-  double acc_zf[ROW_WARPS][MAX_MP];   // backward: per-warp d zf accumulators
-  double acc_th[ROW_WARPS][MAX_THETA]; // backward: per-warp d theta accumulators (scalars | l1 | l2)
+  double acc_zf[BWD ? NW : 1][MAX_MP];      // backward: per-warp d zf accumulators
+  double acc_th[BWD ? NW : 1][MAX_THETA];   // backward: per-warp d theta accumulators (scalars | l1 | l2)
 };
+
+struct RowSmem : CovSmem<ROW_WARPS, false> {
+  double red[3][NCH_MAX][TR];     // per warp-pair partial column sums: q1, mu, q2
+};
+static_assert(ROW_WARPS * RPW == TR, "the covariance build maps RPW rows to each warp of the row tile");
 
 __device__ __forceinline__ double* tile_ptr(unsigned char* smem) {
   return reinterpret_cast<double*>(smem + ((sizeof(RowSmem) + 127) / 128) * 128);
@@ -202,13 +212,14 @@ __device__ __forceinline__ void load_acc_frag(double (&acc)[2][2][4][2], const d
 
 // loads the rows of one tile: x, propagated input f (sample of the previous layer's q(f), the fused
 // reparameterised propagation of layers/mfdgp_hidden_layer.py:263-274), k_xx
-__device__ __forceinline__ void load_tile_rows(const RowArgs& a, RowSmem& sm, long long row0, int nvalid) {
+template <class SM>
+__device__ __forceinline__ void load_tile_rows(const RowArgs& a, SM& sm, long long row0, int nvalid) {
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < TR * a.d; idx += ROW_THREADS) {
+  for (int idx = tid; idx < SM::ROWS * a.d; idx += SM::THREADS) {
     const int r = idx / a.d, c = idx - r * a.d;
     sm.xs[r][c] = r < nvalid ? a.x[(size_t)((row0 + r) / a.xrep) * a.d + c] : 0.0;
   }
-  if (tid < TR) {
+  if (tid < SM::ROWS) {
     double f = 0.0;
     if (tid < nvalid && a.kind == 1) {
       const long long row = row0 + tid;
@@ -246,18 +257,17 @@ __device__ inline void load_kern_fast(KernFast& kf, int kind, int d, const doubl
   for (int c = 0; c < kMaxD; ++c) kf.cc[c] = make_double2(kf.c1[c], kf.c2[c]);
 }
 
-__device__ __forceinline__ void load_inducing(const RowArgs& a, RowSmem& sm) {
+template <class SM>
+__device__ __forceinline__ void load_inducing(const RowArgs& a, SM& sm) {
   const int tid = threadIdx.x;
   if (tid == 0) load_kern_fast(sm.kf, a.kind, a.d, a.theta);
   if (tid >= 32 && tid < 32 + kExp2Tab) sm.e2tab[tid - 32] = exp2((double)(tid - 32) / kExp2Tab);
-  for (int idx = tid; idx < a.MP * a.d; idx += ROW_THREADS) {
+  for (int idx = tid; idx < a.MP * a.d; idx += SM::THREADS) {
     const int j = idx / a.d, c = idx - j * a.d;
     sm.zsT[c][j] = j < a.M ? a.Zx[(size_t)j * a.d + c] : 0.0;
   }
-  for (int j = tid; j < a.MP; j += ROW_THREADS) sm.zfs[j] = (a.kind == 1 && j < a.M) ? a.zf[j] : 0.0;
+  for (int j = tid; j < a.MP; j += SM::THREADS) sm.zfs[j] = (a.kind == 1 && j < a.M) ? a.zf[j] : 0.0;
 }
-
-constexpr int RPW = TR / ROW_WARPS;   // tile rows per warp in the covariance phases
 
 // K(Z_l, rows of the tile) into shared memory: Ks[r][j].  Warp <-> RPW rows, lane <-> inducing point of a 32-chunk;
 // the inducing point stays in registers while the warp's rows (kept in registers too) run past it, which gives RPW
@@ -443,8 +453,8 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
 //   th[0] = sum gk a1 E1 gg  (d/da1 = th[0] / a1)     th[1] = sum gk a1 E1 f f'   (d/dv)
 //   th[2] = sum gk a1 E1 af Ef (d/daf = th[2] / af)   th[3] = sum gk a1 E1 af Ef (f-f')^2  (d/dlf = th[3] / lf^3)
 //   th[4] = sum gk a2 E2     (d/da2 = th[4] / a2)     tl1[c], tl2[c] = sum g D_c^2  (d/dl_c = tl / l_c^3)
-template <int KIND, int D, bool PARAM, bool XGRAD>
-__device__ __forceinline__ void kgrad_tile(const RowArgs& a, RowSmem& sm, const double* __restrict__ Ks, int ldb,
+template <int KIND, int D, bool PARAM, bool XGRAD, class SM>
+__device__ __forceinline__ void kgrad_tile(const RowArgs& a, SM& sm, const double* __restrict__ Ks, int ldb,
                                            long long row0, int nvalid, int warp, int lane) {
   const KernFast& kf = sm.kf;
   const double* tab = sm.e2tab;
@@ -475,7 +485,7 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, RowSmem& sm, const 
     double azf = 0.0;
 #pragma unroll 2
     for (int i = 0; i < RPW; ++i) {
-      const double gk = jok ? Ks[(size_t)(rbase + i) * ldb + j] : 0.0;
+      const double gk = (jok && rbase + i < nvalid) ? Ks[(size_t)(rbase + i) * ldb + j] : 0.0;
       const double fi = sm.fs[rbase + i];
       double diff[D], d2[D], D1 = la1, D2 = la2;
 #pragma unroll
@@ -572,8 +582,8 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, RowSmem& sm, const 
   }
 }
 
-template <int KIND, bool PARAM, bool XGRAD>
-__device__ __forceinline__ void kgrad_tile_d(const RowArgs& a, RowSmem& sm, const double* Ks, int ldb, long long row0,
+template <int KIND, bool PARAM, bool XGRAD, class SM>
+__device__ __forceinline__ void kgrad_tile_d(const RowArgs& a, SM& sm, const double* Ks, int ldb, long long row0,
                                              int nvalid, int warp, int lane) {
   switch (sm.kf.d) {
     case 1: kgrad_tile<KIND, 1, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
@@ -589,16 +599,25 @@ __device__ __forceinline__ void kgrad_tile_d(const RowArgs& a, RowSmem& sm, cons
 
 // ---------------------------------------------------------------------------------------------------
 // backward of the row pass: given d loss/d mu_r, d loss/d var_r
-//   dt = dmu beta - 2 dvar (mask t - H u);  dk = W^T dt
-//   then through the covariance function: d theta, d zf (inducing propagated column), d f_r, d x_r.
+//   dt = dmu beta - 2 dvar (mask t - H u);  dk = W^T dt                    (row_bwd_gemm_kernel, DMMA)
+//   then through the covariance function: d theta, d zf, d f_r, d x_r      (kgrad_kernel, DFMA)
+// The two halves are separate kernels: fused, the covariance gradient's accumulators pushed the products'
+// accumulators into local memory (ncu: 16 of 32 spilled and reloaded every k-step, profiles/r01j_*); apart, the
+// product kernel is the forward kernel's shape and the gradient kernel gets its own register budget and occupancy.
+// dk travels through HBM ([R][MP], written and read once, coalesced).
 // The whitened second-order statistics  A2 = sum_r dvar_r t t^T  and  b = sum_r dmu_r t  (t = W k)
 // are accumulated by syrk_kernel from the saved T and consumed by the operator backward (matrix_ops.cu).
 // ---------------------------------------------------------------------------------------------------
-template <bool PARAM, bool XGRAD>
-__global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_bwd_kernel(const __grid_constant__ RowArgs a) {
+struct BwdSmem {
+  double dmu[TR], dvar[TR], mask[TR];
+};
+__host__ __device__ inline size_t bwd_smem_bytes(int MP) { return 1024 + (size_t)TR * (MP + 4) * sizeof(double); }
+
+__global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_bwd_gemm_kernel(const __grid_constant__ RowArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  RowSmem& sm = *reinterpret_cast<RowSmem*>(smem_raw);
-  double* Ks = tile_ptr(smem_raw);
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+  double* Ks = reinterpret_cast<double*>(smem_raw + 1024);
+  static_assert(sizeof(BwdSmem) <= 1024, "BwdSmem");
   const int MP = a.MP, ldb = MP + 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int half = warp % NHALF, p = warp / NHALF;
@@ -610,18 +629,11 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_bwd_kernel(c
   const double* WT = a.ops + ops_block(MP, OPS_WT);
   const double* H = a.ops + ops_block(MP, OPS_H);
   const double* beta = a.ops + ops_beta(MP);
-  const int d = a.d;
-
-  load_inducing(a, sm);
-  for (int j = lane; j < MAX_MP; j += 32) sm.acc_zf[warp][j] = 0.0;
-  if (lane < MAX_THETA) sm.acc_th[warp][lane] = 0.0;
-  __syncthreads();
 
   const long long ntiles = (a.R + TR - 1) / TR;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row0 = tile * TR;
     const int nvalid = (int)min((long long)TR, a.R - row0);
-    load_tile_rows(a, sm, row0, nvalid);
     if (tid < TR) {
       const bool ok = tid < nvalid;
       sm.dmu[tid] = ok ? a.dmu[row0 + tid] : 0.0;
@@ -635,7 +647,7 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_bwd_kernel(c
       store_acc_to_tile(acc, Ks, ldb, sA, sB, half, lane);
     }
     __syncthreads();
-    // ---- y = H u ;  dt = dmu beta - 2 dvar (mask t - y) ----
+    // ---- y = H u ----
     if (active) {
       zero_acc(acc);
       slab_gemm<false>(acc, H, MP, Ks, ldb, sA, sB, half, lane);
@@ -645,6 +657,7 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_bwd_kernel(c
       for (int j = lane; j < MP; j += 32)
         Ks[(size_t)r * ldb + j] = r < nvalid ? a.Tsave[(size_t)(row0 + r) * MP + j] : 0.0;
     __syncthreads();
+    // ---- dt = dmu beta - 2 dvar (mask t - y) ----
     if (active) {
 #pragma unroll
       for (int sl = 0; sl < 2; ++sl)
@@ -673,22 +686,55 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_bwd_kernel(c
     __syncthreads();
     if (active) store_acc_to_tile(acc, Ks, ldb, sA, sB, half, lane);
     __syncthreads();
-    // ---- through the covariance function ----
-    if (a.kind == 0) kgrad_tile_d<0, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane);
-    else kgrad_tile_d<1, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane);
+    for (int r = warp; r < nvalid; r += ROW_WARPS)
+      for (int j = lane; j < MP; j += 32) a.dk[(size_t)(row0 + r) * MP + j] = Ks[(size_t)r * ldb + j];
+    __syncthreads();
+  }
+}
+
+// ---- through the covariance function: 4 warps x RPW rows per tile, 3 CTAs per SM ----
+constexpr int KG_WARPS = 4, KG_THREADS = KG_WARPS * 32, KG_ROWS = KG_WARPS * RPW, KG_CTAS_PER_SM = 3;
+using KgSmem = CovSmem<KG_WARPS, true>;
+
+template <bool PARAM, bool XGRAD>
+__global__ void __launch_bounds__(KG_THREADS, KG_CTAS_PER_SM) kgrad_kernel(const __grid_constant__ RowArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  KgSmem& sm = *reinterpret_cast<KgSmem*>(smem_raw);
+  const int MP = a.MP, d = a.d;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  load_inducing(a, sm);
+  for (int j = lane; j < MAX_MP; j += 32) sm.acc_zf[warp][j] = 0.0;
+  if (lane < MAX_THETA) sm.acc_th[warp][lane] = 0.0;
+  __syncthreads();
+
+  const long long ntiles = (a.R + KG_ROWS - 1) / KG_ROWS;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * KG_ROWS;
+    const int nvalid = (int)min((long long)KG_ROWS, a.R - row0);
+    load_tile_rows(a, sm, row0, nvalid);
+    if (tid < KG_ROWS) {
+      const bool ok = tid < nvalid;
+      sm.dvar[tid] = ok ? a.dvar[row0 + tid] : 0.0;
+      sm.mask[tid] = (ok && a.training && a.craw) ? (a.craw[row0 + tid] >= 0.0 ? 1.0 : 0.0) : 1.0;
+    }
+    __syncthreads();
+    const double* dk = a.dk + (size_t)row0 * MP;
+    if (a.kind == 0) kgrad_tile_d<0, PARAM, XGRAD>(a, sm, dk, MP, row0, nvalid, warp, lane);
+    else kgrad_tile_d<1, PARAM, XGRAD>(a, sm, dk, MP, row0, nvalid, warp, lane);
     __syncthreads();
   }
   if (PARAM) {
     // ---- flush the per-CTA partials (fixed summation order -> deterministic) ----
     __syncthreads();
-    for (int j = tid; j < MP; j += ROW_THREADS) {
+    for (int j = tid; j < MP; j += KG_THREADS) {
       double s = 0.0;
-      for (int w = 0; w < ROW_WARPS; ++w) s += sm.acc_zf[w][j];
+      for (int w = 0; w < KG_WARPS; ++w) s += sm.acc_zf[w][j];
       a.part_zf[(size_t)blockIdx.x * MP + j] = s;
     }
     if (tid < MAX_THETA) {
       double s = 0.0;
-      for (int w = 0; w < ROW_WARPS; ++w) s += sm.acc_th[w][tid];
+      for (int w = 0; w < KG_WARPS; ++w) s += sm.acc_th[w][tid];
       // map (scalars | l1 | l2) accumulators to the theta layout and undo the accumulator scalings (see kgrad_tile)
       const KernFast& kf = sm.kf;
       double out = 0.0;
@@ -905,24 +951,35 @@ int launch_row_fwd(const RowArgs& a, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-int launch_row_bwd(const RowArgs& a, int grid, cudaStream_t st) {
+int kgrad_grid(long long R) {
+  const long long ntiles = (R + KG_ROWS - 1) / KG_ROWS;
+  const long long cap = (long long)num_sms() * KG_CTAS_PER_SM;
+  return (int)(ntiles < cap ? (ntiles > 0 ? ntiles : 1) : cap);
+}
+
+// product kernel (dk into a.dk) followed by the covariance-gradient kernel; per-CTA partials of the latter are
+// indexed by ITS grid (kgrad_grid)
+int launch_row_bwd(const RowArgs& a, cudaStream_t st) {
   if (a.MP % 32 != 0 || a.MP > MAX_MP || a.d > kMaxD || a.M > a.MP) return -2;
-  const size_t smem = row_smem_bytes(a.MP);
   static bool attr_done = false;
   if (!attr_done) {
-    const int mx = (int)row_smem_bytes(MAX_MP);
-    cudaFuncSetAttribute(row_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(row_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(row_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(row_bwd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(MAX_MP));
+    cudaFuncSetAttribute(kgrad_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KgSmem));
+    cudaFuncSetAttribute(kgrad_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KgSmem));
+    cudaFuncSetAttribute(kgrad_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KgSmem));
     attr_done = true;
   }
   if (a.R <= 0) return 0;
+  MOBO_LAUNCH("row_bwd_gemm_kernel", st,
+              row_bwd_gemm_kernel<<<row_grid(a.R), ROW_THREADS, bwd_smem_bytes(a.MP), st>>>(a));
+  const int grid = kgrad_grid(a.R);
+  const size_t smem = sizeof(KgSmem);
   if (a.want_param_grads && a.want_x_grads) {
-    MOBO_LAUNCH("row_bwd_kernel<param,x>", st, row_bwd_kernel<true, true><<<grid, ROW_THREADS, smem, st>>>(a));
+    MOBO_LAUNCH("kgrad_kernel<param,x>", st, kgrad_kernel<true, true><<<grid, KG_THREADS, smem, st>>>(a));
   } else if (a.want_x_grads) {
-    MOBO_LAUNCH("row_bwd_kernel<x>", st, row_bwd_kernel<false, true><<<grid, ROW_THREADS, smem, st>>>(a));
+    MOBO_LAUNCH("kgrad_kernel<x>", st, kgrad_kernel<false, true><<<grid, KG_THREADS, smem, st>>>(a));
   } else {
-    MOBO_LAUNCH("row_bwd_kernel<param>", st, row_bwd_kernel<true, false><<<grid, ROW_THREADS, smem, st>>>(a));
+    MOBO_LAUNCH("kgrad_kernel<param>", st, kgrad_kernel<true, false><<<grid, KG_THREADS, smem, st>>>(a));
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
