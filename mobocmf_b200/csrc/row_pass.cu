@@ -272,20 +272,23 @@ __device__ __forceinline__ void load_inducing(const RowArgs& a, SM& sm) {
 // K(Z_l, rows of the tile) into shared memory: Ks[r][j].  Warp <-> RPW rows, lane <-> inducing point of a 32-chunk;
 // the inducing point stays in registers while the warp's rows (kept in registers too) run past it, which gives RPW
 // independent exponent chains per thread.
-template <int KIND, int D>
+// SHX: the warp's RPW rows are MC samples of the same point (same x, different propagated f): the two x-kernels
+// a1 E1 and a2 E2 are then evaluated once per inducing point instead of once per row (the S-sample tiling of
+// models/mfdgp.py:248 makes this the common case for layers >= 1).
+template <int KIND, int D, bool SHX>
 __device__ __forceinline__ void build_k_tile(const RowSmem& sm, double* __restrict__ Ks, int ldb, int M, int MP,
                                              int nvalid, int warp, int lane) {
   const KernFast& kf = sm.kf;
   const double* tab = sm.e2tab;
   const int rbase = warp * RPW;
-  double x[RPW][D], f[RPW], vf[RPW], c1[D], c2[D];
+  constexpr int NX = SHX ? 1 : RPW;
+  double x[NX][D], f[RPW], vf[RPW], c1[D], c2[D];
 #pragma unroll
-  for (int i = 0; i < RPW; ++i) {
+  for (int i = 0; i < NX; ++i)
 #pragma unroll
     for (int c = 0; c < D; ++c) x[i][c] = sm.xs[rbase + i][c];
-    f[i] = sm.fs[rbase + i];
-    vf[i] = kf.vlin * f[i];
-  }
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) { f[i] = sm.fs[rbase + i]; vf[i] = kf.vlin * f[i]; }
 #pragma unroll
   for (int c = 0; c < D; ++c) { c1[c] = kf.c1[c]; c2[c] = kf.c2[c]; }
   const double la1 = kf.la1, la2 = kf.la2, laf = kf.laf, cf = kf.cf;
@@ -296,42 +299,53 @@ __device__ __forceinline__ void build_k_tile(const RowSmem& sm, double* __restri
     for (int c = 0; c < D; ++c) z[c] = sm.zsT[c][j];
     const double zf = sm.zfs[j];
     const bool jok = j < M;
+    double s1 = 0.0, s2 = 0.0;
 #pragma unroll
     for (int i = 0; i < RPW; ++i) {
-      double D1 = la1, D2 = la2;
+      if (!SHX || i == 0) {
+        double D1 = la1, D2 = la2;
 #pragma unroll
-      for (int c = 0; c < D; ++c) {
-        const double df = x[i][c] - z[c];
-        const double d2 = df * df;
-        D1 = fma(d2, c1[c], D1);
-        if (KIND == 1) D2 = fma(d2, c2[c], D2);
+        for (int c = 0; c < D; ++c) {
+          const double df = x[SHX ? 0 : i][c] - z[c];
+          const double d2 = df * df;
+          D1 = fma(d2, c1[c], D1);
+          if (KIND == 1) D2 = fma(d2, c2[c], D2);
+        }
+        s1 = exp2_tab(D1, tab);
+        if (KIND == 1) s2 = exp2_tab(D2, tab);
       }
       double k;
       if (KIND == 0) {
-        k = exp2_tab(D1, tab);
+        k = s1;
       } else {
         const double dff = f[i] - zf;
         const double Ef = exp2_tab(fma(dff * dff, cf, laf), tab);
-        k = fma(exp2_tab(D1, tab), fma(vf[i], zf, Ef), exp2_tab(D2, tab));
+        k = fma(s1, fma(vf[i], zf, Ef), s2);
       }
       Ks[(size_t)(rbase + i) * ldb + j] = (jok && rbase + i < nvalid) ? k : 0.0;
     }
   }
 }
 
-template <int KIND>
+template <int KIND, bool SHX>
 __device__ __forceinline__ void build_k_tile_d(const RowSmem& sm, double* Ks, int ldb, int M, int MP, int nvalid,
                                                int warp, int lane) {
   switch (sm.kf.d) {
-    case 1: build_k_tile<KIND, 1>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
-    case 2: build_k_tile<KIND, 2>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
-    case 3: build_k_tile<KIND, 3>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
-    case 4: build_k_tile<KIND, 4>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
-    case 5: build_k_tile<KIND, 5>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
-    case 6: build_k_tile<KIND, 6>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
-    case 7: build_k_tile<KIND, 7>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
-    default: build_k_tile<KIND, 8>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    case 1: build_k_tile<KIND, 1, SHX>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    case 2: build_k_tile<KIND, 2, SHX>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    case 3: build_k_tile<KIND, 3, SHX>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    case 4: build_k_tile<KIND, 4, SHX>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    case 5: build_k_tile<KIND, 5, SHX>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    case 6: build_k_tile<KIND, 6, SHX>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    case 7: build_k_tile<KIND, 7, SHX>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
+    default: build_k_tile<KIND, 8, SHX>(sm, Ks, ldb, M, MP, nvalid, warp, lane); break;
   }
+}
+
+// true when the RPW rows of this warp read the same x row (row r reads x[r / xrep])
+__device__ __forceinline__ bool warp_rows_share_x(const RowArgs& a, long long row0, int warp) {
+  const long long r0 = row0 + (long long)warp * RPW;
+  return a.xrep > 1 && r0 / a.xrep == (r0 + RPW - 1) / a.xrep;
 }
 
 __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(const __grid_constant__ RowArgs a) {
@@ -360,8 +374,9 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
     load_tile_rows(a, sm, row0, nvalid);
     __syncthreads();
     // ---- K(Z_l, rows) into shared memory ----
-    if (a.kind == 0) build_k_tile_d<0>(sm, Ks, ldb, a.M, MP, nvalid, warp, lane);
-    else build_k_tile_d<1>(sm, Ks, ldb, a.M, MP, nvalid, warp, lane);
+    if (a.kind == 0) build_k_tile_d<0, false>(sm, Ks, ldb, a.M, MP, nvalid, warp, lane);
+    else if (warp_rows_share_x(a, row0, warp)) build_k_tile_d<1, true>(sm, Ks, ldb, a.M, MP, nvalid, warp, lane);
+    else build_k_tile_d<1, false>(sm, Ks, ldb, a.M, MP, nvalid, warp, lane);
     __syncthreads();
     // ---- t = W k ----
     double acc[2][2][4][2];
@@ -453,7 +468,7 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
 //   th[0] = sum gk a1 E1 gg  (d/da1 = th[0] / a1)     th[1] = sum gk a1 E1 f f'   (d/dv)
 //   th[2] = sum gk a1 E1 af Ef (d/daf = th[2] / af)   th[3] = sum gk a1 E1 af Ef (f-f')^2  (d/dlf = th[3] / lf^3)
 //   th[4] = sum gk a2 E2     (d/da2 = th[4] / a2)     tl1[c], tl2[c] = sum g D_c^2  (d/dl_c = tl / l_c^3)
-template <int KIND, int D, bool PARAM, bool XGRAD, class SM>
+template <int KIND, int D, bool PARAM, bool XGRAD, bool SHX, class SM>
 __device__ __forceinline__ void kgrad_tile(const RowArgs& a, SM& sm, const double* __restrict__ Ks, int ldb,
                                            long long row0, int nvalid, int warp, int lane) {
   const KernFast& kf = sm.kf;
@@ -483,6 +498,50 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, SM& sm, const doubl
     const double zf = sm.zfs[j], vz = vlin * zf;
     const bool jok = j < M;
     double azf = 0.0;
+    if (SHX && KIND == 1) {
+      // the warp's rows share x: distances, a1 E1 and a2 E2 once per inducing point; the lengthscale (and x)
+      // gradients take the row-summed weights
+      double diff[D], d2[D], D1 = la1, D2 = la2;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double2 cc = kf.cc[c];
+        diff[c] = sm.xs[rbase][c] - z[c];
+        d2[c] = diff[c] * diff[c];
+        D1 = fma(d2[c], cc.x, D1);
+        D2 = fma(d2[c], cc.y, D2);
+      }
+      const double s1 = exp2_tab(D1, tab), s2 = exp2_tab(D2, tab);
+      double G1 = 0.0, G2 = 0.0;
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const double gk = (jok && rbase + i < nvalid) ? Ks[(size_t)(rbase + i) * ldb + j] : 0.0;
+        const double fi = sm.fs[rbase + i];
+        const double dff = fi - zf, dff2 = dff * dff;
+        const double Efp = exp2_tab(fma(dff2, cf, laf), tab);
+        const double fz = fi * zf;
+        const double gg = fma(vlin, fz, Efp);
+        const double gs1 = gk * s1, g2 = gk * s2;
+        const double g1 = gs1 * gg, gEf = gs1 * Efp;
+        const double q = gEf * (dff * ilf);
+        rdf[i] += fma(gs1, vz, -q);
+        G1 += g1; G2 += g2;
+        if (PARAM) {
+          azf += fma(gs1, vlin * fi, q);
+          th[1] = fma(gs1, fz, th[1]);
+          th[2] += gEf;
+          th[3] = fma(gEf, dff2, th[3]);
+        }
+      }
+      if (PARAM) {
+        th[0] += G1; th[4] += G2;
+#pragma unroll
+        for (int c = 0; c < D; ++c) { tl1[c] = fma(G1, d2[c], tl1[c]); tl2[c] = fma(G2, d2[c], tl2[c]); }
+      }
+      if (XGRAD) {   // d loss / d x of the shared point: booked on the warp's first row, the others stay zero
+#pragma unroll
+        for (int c = 0; c < D; ++c) rdx[0][c] -= diff[c] * fma(G1, kf.il1[c], G2 * kf.il2[c]);
+      }
+    } else {
 #pragma unroll 2
     for (int i = 0; i < RPW; ++i) {
       const double gk = (jok && rbase + i < nvalid) ? Ks[(size_t)(rbase + i) * ldb + j] : 0.0;
@@ -533,6 +592,7 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, SM& sm, const doubl
         }
       }
     }
+    }
     if (PARAM && KIND == 1) sm.acc_zf[warp][j] += azf;   // one owner per slot -> deterministic
   }
   // row-wise sums over the inducing points, and the diag term d k_xx of the variance
@@ -582,18 +642,18 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, SM& sm, const doubl
   }
 }
 
-template <int KIND, bool PARAM, bool XGRAD, class SM>
+template <int KIND, bool PARAM, bool XGRAD, bool SHX, class SM>
 __device__ __forceinline__ void kgrad_tile_d(const RowArgs& a, SM& sm, const double* Ks, int ldb, long long row0,
                                              int nvalid, int warp, int lane) {
   switch (sm.kf.d) {
-    case 1: kgrad_tile<KIND, 1, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    case 2: kgrad_tile<KIND, 2, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    case 3: kgrad_tile<KIND, 3, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    case 4: kgrad_tile<KIND, 4, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    case 5: kgrad_tile<KIND, 5, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    case 6: kgrad_tile<KIND, 6, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    case 7: kgrad_tile<KIND, 7, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    default: kgrad_tile<KIND, 8, PARAM, XGRAD>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 1: kgrad_tile<KIND, 1, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 2: kgrad_tile<KIND, 2, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 3: kgrad_tile<KIND, 3, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 4: kgrad_tile<KIND, 4, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 5: kgrad_tile<KIND, 5, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 6: kgrad_tile<KIND, 6, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 7: kgrad_tile<KIND, 7, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    default: kgrad_tile<KIND, 8, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
   }
 }
 
@@ -720,8 +780,9 @@ __global__ void __launch_bounds__(KG_THREADS, KG_CTAS_PER_SM) kgrad_kernel(const
     }
     __syncthreads();
     const double* dk = a.dk + (size_t)row0 * MP;
-    if (a.kind == 0) kgrad_tile_d<0, PARAM, XGRAD>(a, sm, dk, MP, row0, nvalid, warp, lane);
-    else kgrad_tile_d<1, PARAM, XGRAD>(a, sm, dk, MP, row0, nvalid, warp, lane);
+    if (a.kind == 0) kgrad_tile_d<0, PARAM, XGRAD, false>(a, sm, dk, MP, row0, nvalid, warp, lane);
+    else if (warp_rows_share_x(a, row0, warp)) kgrad_tile_d<1, PARAM, XGRAD, true>(a, sm, dk, MP, row0, nvalid, warp, lane);
+    else kgrad_tile_d<1, PARAM, XGRAD, false>(a, sm, dk, MP, row0, nvalid, warp, lane);
     __syncthreads();
   }
   if (PARAM) {
