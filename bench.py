@@ -153,16 +153,43 @@ def run_ours(args):
         idx = torch.randint(0, N, (B,), device=dev, generator=g)
         return one_step(xd[idx], yd[idx], fd[idx])
 
-    hb = [torch.empty(B, cfg["d"], dtype=torch.float64).pin_memory(), torch.empty(B, 1, dtype=torch.float64).pin_memory(),
-          torch.empty(B, 1, dtype=torch.float64).pin_memory()]
+    # two pinned staging sets: the host fills set i % 2 while the copies of step i - 1 may still be in flight; set
+    # i % 2 was last used by step i - 2, whose loss has been consumed (so its copies are complete) by then
+    hbs = [[torch.empty(B, cfg["d"], dtype=torch.float64).pin_memory(), torch.empty(B, 1, dtype=torch.float64).pin_memory(),
+            torch.empty(B, 1, dtype=torch.float64).pin_memory()] for _ in range(2)]
     gh = torch.Generator().manual_seed(99 + rank)
 
+    # End-to-end arm: every step copies ITS minibatch from pinned host memory (H2D inside the timed region) and the
+    # step's loss comes back to pinned host memory (D2H).  The loss of step i is consumed by the host while step
+    # i + 1 is already enqueued (a one-deep prefetch, like any data loader), so the GPU never waits for Python;
+    # the last loss is read inside the timed region too.
+    loss_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+    pending = []
+    e2e_losses = []
+
     def e2e_step():
+        slot = len(e2e_losses) % 2
+        hb = hbs[slot]
         idx = torch.randint(0, N, (B,), generator=gh)
         torch.index_select(xh, 0, idx, out=hb[0]); torch.index_select(yh, 0, idx, out=hb[1])
         torch.index_select(fh, 0, idx, out=hb[2])
         xb, yb, fb = (t.to(dev, non_blocking=True) for t in hb)
-        return float(one_step(xb, yb, fb).detach())       # device -> host read of the step's loss
+        loss = one_step(xb, yb, fb)
+        if pending:                       # consume the previous step's loss before its slot can be reused
+            ev, sl = pending.pop()
+            ev.synchronize()
+            e2e_losses[-1] = float(loss_host[sl])
+        loss_host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        pending.append((ev, slot))
+        e2e_losses.append(None)
+
+    def e2e_drain():
+        if pending:
+            ev, sl = pending.pop()
+            ev.synchronize()
+            e2e_losses[-1] = float(loss_host[sl])
 
     def barrier():
         if world > 1:
@@ -194,7 +221,23 @@ def run_ours(args):
         sampler.stop_flag = True
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    e2e_drain()
+
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_drain()                            # the last step's loss is on the host before the clock stops
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms_e2e = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms_e2e)
+    assert all(v is not None and math.isfinite(v) for v in e2e_losses[-args.steps:])
 
     # per-kernel CUDA-event timing of a few extra steps (launch stream = torch's current stream)
     prof = {}
@@ -225,24 +268,42 @@ def run_ours(args):
                        "global_batch": world * B, "parallelism": "dp%d rows sharded, grads all-reduced" % world,
                        "cache": "per-step working set (3 x 134 MB saved tiles per upper layer) exceeds L2"},
             "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": "steps/s",
-                    "h2d_bytes_per_step": B * (cfg["d"] + 2) * 8, "d2h_bytes_per_step": 8},
+                    "h2d_bytes_per_step": B * (cfg["d"] + 2) * 8, "d2h_bytes_per_step": 8,
+                    "note": "host minibatch -> pinned H2D -> fused step + Adam -> loss D2H, every step; the loss of "
+                            "step i is read while step i+1 is enqueued"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary() if sampler else None,
             "step_tflops": flops / (ms_step * 1e-3) / 1e12,
         }
         if prof:
             tot = {k: sum(v) for k, v in prof.items()}
-            top = max((k for k in tot if k.startswith("row_")), key=lambda k: tot[k])
-            per_launch_ms = tot[top] / len(prof[top])
-            rows = B * S
-            alg = (1 if "fwd" in top else 2) * f1 * rows        # forward F per row; backward = 2 F per row
-            out["roofline"] = {"bound": "tensor", "kernel": top, "achieved": alg / (per_launch_ms * 1e-3) / 1e12,
-                               "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                               "frac": alg / (per_launch_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS, "traffic": None,
-                               "peak_source": "measured DMMA fp64 pipe peak, profiles/r01_fp64_probe.log "
-                                              "(MEASURED_PEAKS.json has no fp64 figure)",
-                               "launch_ms": per_launch_ms}
             nst = min(args.steps, 5)
+            # dominant kernel = the one of OUR kernels with the largest share of the step; its algorithmic flops are
+            # summed over its launches of a step (layer 0 runs on B rows, the upper layers on B*S) and divided by the
+            # summed launch durations (DESIGN.md section 2 "Roofline numerator")
+            M, d, L = cfg["M"], cfg["d"], cfg["L"]
+            rows = [B] + [B * S] * (L - 1)
+            dl = [d] + [d + 1] * (L - 1)
+            alg_per_step = {
+                "row_fwd_kernel": sum(r * (2 * M * M + 2 * M + 3 * k * M) for r, k in zip(rows, dl)),
+                "row_bwd_gemm_kernel": sum(r * (2 * M * M + 2 * M) for r in rows),
+                "syrk_kernel": sum(r * M * M for r in rows),
+            }
+            top = max((k for k in tot if k in alg_per_step), key=lambda k: tot[k])
+            ms_top = tot[top] / nst
+            achieved = alg_per_step[top] / (ms_top * 1e-3) / 1e12
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get(top)
+            out["roofline"] = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
+                               "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
+                               "peak_source": "measured DMMA fp64 pipe peak (mma.sync.m8n8k4.f64), "
+                                              "profiles/r01_fp64_probe.log; MEASURED_PEAKS.json has no fp64 figure "
+                                              "(cuBLAS DGEMM on the same pool: 35.4)",
+                               "launches_per_step": len(prof[top]) // nst, "ms_per_step": ms_top,
+                               "algorithmic_gflop_per_step": alg_per_step[top] / 1e9,
+                               "share_of_step": ms_top / ms_step}
             out["kernel_ms_per_step"] = {k: round(v / nst, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}
         if acq:
             out["acq"] = acq

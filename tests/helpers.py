@@ -124,3 +124,28 @@ def parity_tol(model, base=1e-10):
         P = O.layer_kernel(sd, l, Z, Z) + O.JITTER * torch.eye(Z.shape[0], dtype=torch.float64)
         worst = max(worst, float(torch.linalg.cond(P)))
     return max(base, 20 * 2.2e-16 * worst), worst
+
+
+def model_from_state(sd, noise_upper, L, samples=None, device="cuda:0", noise_lower=None):
+    """A product MFDGP whose parameters, inducing inputs, noise bounds (and eval samples) equal the given oracle
+    state: the bridge from golden vectors / random states to the drop-in classes."""
+    from mobocmf_b200.models.mfdgp import MFDGP
+    Zx = sd["hidden_layer_0.variational_strategy.inducing_points"]
+    M, d = Zx.shape
+    fid = (torch.arange(M) % L).double()[:, None]
+    y = torch.linspace(-1.0, 1.0, M, dtype=torch.float64)[:, None]
+    model = MFDGP(Zx.clone(), y, fid, L, init_lengthscale=0.5)
+    model.double()
+    own = model.state_dict()
+    with torch.no_grad():
+        for k, v in sd.items():
+            if k in own and "inducing_points" not in k:
+                own[k].copy_(v.reshape(own[k].shape))
+        for l in range(L):
+            c = getattr(model, "hidden_layer_likelihood_%d" % l).noise_covar.raw_noise_constraint
+            c.upper_bound.copy_(torch.as_tensor(noise_upper[l], dtype=torch.float64))
+            c.lower_bound.copy_(torch.as_tensor(O.NOISE_LOWER if noise_lower is None else noise_lower[l],
+                                                dtype=torch.float64))
+            if samples is not None:
+                getattr(model, "hidden_layer_%d" % l).samples = samples[l].clone()
+    return model.to(device)
