@@ -147,5 +147,8 @@ def model_from_state(sd, noise_upper, L, samples=None, device="cuda:0", noise_lo
             c.lower_bound.copy_(torch.as_tensor(O.NOISE_LOWER if noise_lower is None else noise_lower[l],
                                                 dtype=torch.float64))
             if samples is not None:
-                getattr(model, "hidden_layer_%d" % l).samples = samples[l].clone()
+                layer = getattr(model, "hidden_layer_%d" % l)
+                layer.samples = samples[l].clone()
+                layer.num_samples_for_acquisition = samples[l].shape[0]
+                model.num_samples_for_acquisition = samples[l].shape[0]
     return model.to(device)
