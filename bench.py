@@ -241,12 +241,13 @@ def run_ours(args):
 
     # per-kernel CUDA-event timing of a few extra steps (launch stream = torch's current stream)
     prof = {}
+    nprof = min(args.steps, 5)
     if rank == 0:
         _lib.profile_enable(True)
-        nprof = min(args.steps, 5)
-        for _ in range(nprof):
-            device_step()
-        torch.cuda.synchronize()
+    for _ in range(nprof):            # every rank steps (the step contains the gradient all-reduce); rank 0 records
+        device_step()
+    torch.cuda.synchronize()
+    if rank == 0:
         for name, t in _lib.profile_collect():
             prof.setdefault(name, []).append(t)
         _lib.profile_enable(False)
@@ -307,7 +308,7 @@ def run_ours(args):
             out["kernel_ms_per_step"] = {k: round(v / nst, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}
         if acq:
             out["acq"] = acq
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:      # reported on rank 0 at N = 1 only
             out["cpu_baseline"] = cpu_baseline(cfg, x, y, fid, model)
         print(json.dumps(out))
     if world > 1:
@@ -345,6 +346,7 @@ def cpu_baseline(cfg, x, y, fid, model, max_seconds=30.0):
     sample of the same workload: same model / B / M, S reduced to S_cpu and scaled by rows."""
     from oracle import mfdgp_oracle as O
     from tests.helpers import oracle_view
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     sd, lo, up, _ = oracle_view(model)
     names = [n for n, p in model.named_parameters() if p.requires_grad]
     for n in names:
