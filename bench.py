@@ -308,11 +308,64 @@ def run_ours(args):
             out["kernel_ms_per_step"] = {k: round(v / nst, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}
         if acq:
             out["acq"] = acq
+        if not args.no_acq:
+            out["small_configs"] = bench_small_configs(dev)
         if not args.no_cpu and world == 1:      # reported on rank 0 at N = 1 only
             out["cpu_baseline"] = cpu_baseline(cfg, x, y, fid, model)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_small_configs(dev, steps=200):
+    """The reference's own (launch-latency-bound) configurations: full-batch ELBO step + Adam, one MC sample, through
+    the fitter's hot loop body, eager fused enqueue vs one CUDA-graph launch per step.
+    C2 = Forrester (d=1, 2 fidelities, N=M=B=16, examples/example_acquisition_mfdgp_forrester); C1/C3-sized = d=2,
+    2 fidelities, N=M=B=75 (the toy / synthetic-2D runs at their largest)."""
+    from mobocmf_b200.fused import Adam, FusedELBOStep, GraphedELBOStep
+    from mobocmf_b200.mlls.variational_elbo_mf import VariationalELBOMF
+    from mobocmf_b200.models.mfdgp import MFDGP
+    from tests.helpers import forrester_data, synthetic_data
+    out = {}
+    for name in ("C2_forrester_N16", "C1C3_sized_N75"):
+        if name.startswith("C2"):
+            x, ys, fid = forrester_data()
+            y = ys["obj1"]
+        else:
+            x, y, fid = synthetic_data([50, 25], 2, seed=4)
+        N = x.shape[0]
+        res = {}
+        for mode in ("eager", "graph"):
+            torch.manual_seed(0)
+            model = MFDGP(x, y, fid, 2)
+            model.double().to(dev)
+            elbo = VariationalELBOMF(model, N, 2)
+            model.fix_variational_hypers(False)
+            opt = Adam([{"params": model.parameters()}], lr=0.001, capturable=(mode == "graph"))
+            fstep = FusedELBOStep(model, elbo)
+            xd, yd, fd = x.to(dev), y.to(dev), fid.to(dev)
+            perm = torch.randperm(N, device=dev)
+            xb, yb, fb = xd[perm], yd[perm], fd[perm]
+            if mode == "graph":
+                gstep = GraphedELBOStep(fstep, opt, N)
+                fn = lambda: gstep(xb, yb, fb)
+            else:
+                def fn():
+                    fstep(xb, yb, fb, check_shortcut=False)
+                    opt.step()
+            for _ in range(10):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            res[mode + "_us_per_step"] = round(e0.elapsed_time(e1) / steps * 1e3, 1)
+        res["steps_per_s"] = round(1e6 / res["graph_us_per_step"], 1)
+        out[name] = res
+    return out
 
 
 def bench_acq(model, dev, cfg, n=20000, iters=3):

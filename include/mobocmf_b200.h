@@ -150,10 +150,13 @@ size_t mobo_elbo_step_workspace_doubles(int L, int d, int M, int S, long long B)
 int mobo_elbo_step(const mobo_step_desc* desc, void* stream);
 
 /* torch.optim.Adam update (mobocmf/util/blackbox_mfdgp_fitter.py:126,132,259; defaults betas (0.9, 0.999),
- * eps 1e-8, no weight decay) of nt <= 64 tensors in one launch.  step = 1-based step count after increment. */
+ * eps 1e-8, no weight decay) of nt <= 64 tensors in one launch.  step = 1-based step count after increment, or, for
+ * CUDA-graph replays, step_dev != NULL: a device-resident count (advance it with mobo_adam_tick before each update;
+ * `step` is then ignored). */
 typedef struct mobo_adam_tensor { double* p; const double* g; double* exp_avg; double* exp_avg_sq; long long n; } mobo_adam_tensor;
 int mobo_adam(int nt, const mobo_adam_tensor* tensors, double lr, double beta1, double beta2, double eps,
-              long long step, void* stream);
+              long long step, long long* step_dev, void* stream);
+int mobo_adam_tick(long long* step_dev, void* stream);
 
 /* Acquisition chain of ONE MFDGP in eval mode: MFDGP.predict_for_acquisition (mobocmf/models/mfdgp.py:237-262) for n
  * candidates x S fixed normals per layer, up to layer `fidelity`, from precomputed operator buffers (the parameters

@@ -460,13 +460,13 @@ int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
 }
 
 int mobo_adam(int nt, const mobo_adam_tensor* tensors, double lr, double beta1, double beta2, double eps,
-              long long step, void* stream) {
-  if (nt < 1 || nt > ADAM_MAX_TENSORS || step < 1) return -2;
+              long long step, long long* step_dev, void* stream) {
+  if (nt < 1 || nt > ADAM_MAX_TENSORS || (step < 1 && !step_dev)) return -2;
   cudaStream_t st = (cudaStream_t)stream;
   AdamArgs a;
-  a.nt = nt; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
-  a.bc1 = 1.0 - pow(beta1, (double)step);
-  a.bc2_sqrt = sqrt(1.0 - pow(beta2, (double)step));
+  a.nt = nt; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.step_dev = step_dev;
+  a.bc1 = step_dev ? 1.0 : 1.0 - pow(beta1, (double)step);
+  a.bc2_sqrt = step_dev ? 1.0 : sqrt(1.0 - pow(beta2, (double)step));
   long long mx = 1;
   for (int i = 0; i < ADAM_MAX_TENSORS; ++i) {
     const bool ok = i < nt;
@@ -478,6 +478,12 @@ int mobo_adam(int nt, const mobo_adam_tensor* tensors, double lr, double beta1, 
   long long gx = (mx + 255) / 256;
   if (gx > 64) gx = 64;
   MOBO_LAUNCH("adam_kernel", st, adam_kernel<<<dim3((unsigned)gx, nt), 256, 0, st>>>(a));
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int mobo_adam_tick(long long* step_dev, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MOBO_LAUNCH("adam_tick_kernel", st, adam_tick_kernel<<<1, 1, 0, st>>>(step_dev));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -199,7 +199,10 @@ struct AdamArgs {
   double* v[ADAM_MAX_TENSORS];
   long long n[ADAM_MAX_TENSORS];
   double lr, beta1, beta2, eps, bc1, bc2_sqrt;
+  const long long* step_dev;     // optional device-resident step count (CUDA-graph replays): overrides bc1 / bc2_sqrt
 };
+
+__global__ void adam_tick_kernel(long long* step_dev) { *step_dev += 1; }
 
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamArgs a) {
   const int t = blockIdx.y;
@@ -208,14 +211,20 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
   const double* __restrict__ g = a.g[t];
   double* __restrict__ m = a.m[t];
   double* __restrict__ v = a.v[t];
-  const double step_size = a.lr / a.bc1;
+  double bc1 = a.bc1, bc2_sqrt = a.bc2_sqrt;
+  if (a.step_dev) {
+    const double st = (double)(*a.step_dev);
+    bc1 = 1.0 - pow(a.beta1, st);
+    bc2_sqrt = sqrt(1.0 - pow(a.beta2, st));
+  }
+  const double step_size = a.lr / bc1;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const double gi = g[i];
     const double mi = a.beta1 * m[i] + (1.0 - a.beta1) * gi;          // exp_avg.lerp_(grad, 1 - beta1)
     const double vi = a.beta2 * v[i] + (1.0 - a.beta2) * gi * gi;     // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
     m[i] = mi;
     v[i] = vi;
-    const double denom = sqrt(vi) / a.bc2_sqrt + a.eps;
+    const double denom = sqrt(vi) / bc2_sqrt + a.eps;
     p[i] -= step_size * (mi / denom);                                 // param.addcdiv_(exp_avg, denom, -step_size)
   }
 }

@@ -172,7 +172,7 @@ class FusedELBOStep(object):
         return not (x_batch.shape[0] == self.M and bool(torch.equal(x_batch, self.layers[0]._Zx())))
 
     # ---- the step ---------------------------------------------------------------------------------------------
-    def __call__(self, x_batch, y_batch, fidelities, eps=None, num_samples=1, accumulate=False):
+    def __call__(self, x_batch, y_batch, fidelities, eps=None, num_samples=1, accumulate=False, check_shortcut=True):
         """Returns (loss = -ELBO, KL * B / N) as 0-d device tensors (views of one result buffer, overwritten by the
         next call) and writes the gradients.  ``eps``: optional list indexed by layer of the training normals
         (B*S values for layers >= 1; reference: float32 ``torch.normal`` of shape (1, B), quirk Q6)."""
@@ -180,7 +180,7 @@ class FusedELBOStep(object):
         S = int(num_samples)
         if x_batch.shape[1] != self.d or y_batch.numel() != B or fidelities.numel() != B:
             raise ValueError("x (B, d), y (B, 1), fidelities (B, 1) expected")
-        if not self.applies(x_batch):
+        if check_shortcut and not self.applies(x_batch):
             raise RuntimeError("x_batch equals the inducing inputs (quirk Q4 shortcut): use the composable path")
         self._prepare()
         D = self._desc
@@ -222,48 +222,150 @@ class FusedELBOStep(object):
 class Adam(torch.optim.Optimizer):
     """``torch.optim.Adam`` (defaults of ``mobocmf/util/blackbox_mfdgp_fitter.py:126,132,259``) with the update of all
     parameters in ONE kernel launch (``mobo_adam``).  State keys match torch's (``step``, ``exp_avg``,
-    ``exp_avg_sq``) so ``state_dict`` round-trips with ``torch.optim.Adam``."""
+    ``exp_avg_sq``) so ``state_dict`` round-trips with ``torch.optim.Adam``.  ``capturable=True`` keeps the step count
+    in a device tensor (like torch's flag of the same name) so that ``step()`` can be captured in a CUDA graph."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
-        self._table = None
-        self._sig = None
+        self.capturable = capturable
+        self._step_dev = None
+        self._tables = {}
 
     def zero_grad(self, set_to_none=False):
         # gradients live in a persistent flat buffer that the fused step overwrites: keep the tensors
         return super().zero_grad(set_to_none=set_to_none)
+
+    def _table(self, gi, chunk):
+        """ctypes table of (param, grad, exp_avg, exp_avg_sq, n) for a chunk of <= 64 parameters, rebuilt only when a
+        pointer changes."""
+        sig = tuple((p.data_ptr(), p.grad.data_ptr()) for p in chunk)
+        key = (gi, id(chunk[0]))
+        hit = self._tables.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        arr = (AdamTensor * len(chunk))()
+        for j, p in enumerate(chunk):
+            st = self.state[p]
+            arr[j].p, arr[j].g = p.data_ptr(), p.grad.data_ptr()
+            arr[j].exp_avg, arr[j].exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+            arr[j].n = p.numel()
+        self._tables[key] = (sig, arr)
+        return arr
 
     @torch.no_grad()
     def step(self, closure=None):
         if closure is not None:
             raise NotImplementedError("closures are not used by the reference's training loops")
         lib = _bind()
-        for group in self.param_groups:
+        ticked = False
+        for gi, group in enumerate(self.param_groups):
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
             for p in ps:
                 st = self.state[p]
                 if not st:
-                    st["step"] = 0
+                    if not (p.is_cuda and p.dtype == torch.float64 and p.is_contiguous() and p.grad.is_contiguous()):
+                        raise RuntimeError("mobocmf_b200.Adam needs contiguous fp64 CUDA parameters (no CPU fallback)")
+                    if self.capturable:
+                        if self._step_dev is None:
+                            self._step_dev = torch.zeros((), dtype=torch.int64, device=p.device)
+                        st["step"] = self._step_dev          # one shared device-resident count
+                    else:
+                        st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                if not (p.is_cuda and p.dtype == torch.float64 and p.is_contiguous() and p.grad.is_contiguous()):
-                    raise RuntimeError("mobocmf_b200.Adam needs contiguous fp64 CUDA parameters (no CPU fallback)")
+            b1, b2 = group["betas"]
+            if self.capturable:
+                if not ticked:
+                    _lib.check(lib.mobo_adam_tick(_lib.ptr(self._step_dev), _lib.stream_ptr()), "mobo_adam_tick")
+                    ticked = True
+                for i in range(0, len(ps), 64):
+                    chunk = ps[i:i + 64]
+                    _lib.check(lib.mobo_adam(len(chunk), self._table(gi, chunk), float(group["lr"]), float(b1),
+                                             float(b2), float(group["eps"]), 0, _lib.ptr(self._step_dev),
+                                             _lib.stream_ptr()), "mobo_adam")
+                continue
             steps = {int(self.state[p]["step"]) for p in ps}
             for step0 in sorted(steps):
                 sel = [p for p in ps if int(self.state[p]["step"]) == step0]
                 for i in range(0, len(sel), 64):
                     chunk = sel[i:i + 64]
-                    arr = (AdamTensor * len(chunk))()
-                    for j, p in enumerate(chunk):
-                        st = self.state[p]
-                        arr[j].p, arr[j].g = p.data_ptr(), p.grad.data_ptr()
-                        arr[j].exp_avg, arr[j].exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
-                        arr[j].n = p.numel()
-                    b1, b2 = group["betas"]
-                    _lib.check(lib.mobo_adam(len(chunk), arr, float(group["lr"]), float(b1), float(b2),
-                                             float(group["eps"]), step0 + 1, _lib.stream_ptr()), "mobo_adam")
+                    _lib.check(lib.mobo_adam(len(chunk), self._table(gi, chunk), float(group["lr"]), float(b1),
+                                             float(b2), float(group["eps"]), step0 + 1, None, _lib.stream_ptr()),
+                               "mobo_adam")
                 for p in sel:
                     self.state[p]["step"] = step0 + 1
         return None
+
+
+class GraphedELBOStep(object):
+    """The fused step + Adam update of one minibatch shape captured ONCE in a CUDA graph and replayed per step: one
+    graph launch instead of ~55 kernel launches.  This is the path for the reference's own configurations (full batch,
+    M = N of a few tens, ``examples/*``), where a step is a few hundred microseconds of launch latency.
+
+    ``optimizer`` must be ``Adam(..., capturable=True)`` over the model's parameters.  The training normals are drawn
+    inside the graph by torch's graph-safe generator, so every replay uses fresh ones."""
+
+    def __init__(self, step, optimizer, batch_size, num_samples=1, warmup=3, static_eps=False):
+        if not isinstance(optimizer, Adam) or not optimizer.capturable:
+            raise ValueError("GraphedELBOStep needs mobocmf_b200.fused.Adam(capturable=True)")
+        self.step, self.optimizer, self.S = step, optimizer, int(num_samples)
+        dev, d = step.device, step.d
+        # static_eps: the caller supplies the training normals on every call (parity tests); otherwise they are drawn
+        # inside the graph
+        self.eps = None
+        if static_eps:
+            self.eps = [None] + [torch.zeros(batch_size * self.S, dtype=torch.float64, device=dev)
+                                 for _ in range(1, step.L)]
+        self.x = torch.zeros(batch_size, d, dtype=torch.float64, device=dev)
+        self.y = torch.zeros(batch_size, 1, dtype=torch.float64, device=dev)
+        self.f = torch.zeros(batch_size, 1, dtype=torch.float64, device=dev)
+        self.graph = None
+        self._warmup = warmup
+
+    def _capture(self):
+        # parameters are NOT stepped during warm-up / capture side effects: snapshot and restore them and the
+        # optimiser state, so that capturing does not count as training steps
+        params = [p for g in self.optimizer.param_groups for p in g["params"]]
+        snap = [p.detach().clone() for p in params]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(self._warmup):
+                self.step(self.x, self.y, self.f, eps=self.eps, num_samples=self.S, check_shortcut=False)
+                self.optimizer.step()
+        torch.cuda.current_stream().wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.kl = self.step(self.x, self.y, self.f, eps=self.eps, num_samples=self.S,
+                                           check_shortcut=False)
+            self.optimizer.step()
+        with torch.no_grad():
+            for p, v in zip(params, snap):
+                p.copy_(v)
+            for p in params:
+                st = self.optimizer.state.get(p)
+                if st:
+                    st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+            self.optimizer._step_dev.zero_()
+
+    def _stage(self, x_batch, y_batch, fidelities, eps):
+        self.x.copy_(x_batch); self.y.copy_(y_batch.reshape(-1, 1)); self.f.copy_(fidelities.reshape(-1, 1))
+        if self.eps is not None:
+            if eps is None:
+                raise ValueError("this graph was built with static_eps=True: pass eps")
+            for l in range(1, self.step.L):
+                self.eps[l].copy_(eps[l].reshape(-1))
+
+    def __call__(self, x_batch, y_batch, fidelities, eps=None):
+        if not self.step.applies(x_batch):
+            raise RuntimeError("x_batch equals the inducing inputs (quirk Q4 shortcut): use the composable path")
+        if self.graph is None:
+            self._stage(x_batch, y_batch, fidelities, eps)
+            self._capture()
+        self._stage(x_batch, y_batch, fidelities, eps)
+        self.graph.replay()
+        for layer in self.step.layers:
+            layer._ops_cache = None
+        return self.loss, self.kl

@@ -66,7 +66,7 @@ class BlackBoxMFDGPFitter():
 
     def __init__(self, num_fidelities, batch_size, lr_1=0.003, lr_2=0.001, num_epochs_1=5000, num_epochs_2=15000,
                  pareto_set_size=50, opt_grid_size=1000, eps=1e-8, decoupled_evals=False,
-                 type_lengthscale=TL.MEDIAN, device=None):
+                 type_lengthscale=TL.MEDIAN, device=None, use_cuda_graph=False):
         self.num_obj = 0
         self.num_con = 0
         self.models_uncond_trained = False
@@ -87,6 +87,9 @@ class BlackBoxMFDGPFitter():
         self.eps = eps
         self.decoupled_evals = decoupled_evals
         self.type_lengthscale = type_lengthscale
+        # one CUDA-graph launch per step instead of ~55 kernel launches: the regime of the reference's examples
+        # (full batch, M = N of a few tens) is launch-latency bound
+        self.use_cuda_graph = use_cuda_graph
         self.pareto_set = None
         self.pareto_front = None
         self.verbose = True
@@ -129,11 +132,29 @@ class BlackBoxMFDGPFitter():
         return cached or None
 
     @staticmethod
+    def _graphed_step(fused, optimizer, batch_size):
+        """CUDA-graph replay of (fused step + Adam) for this minibatch shape; built on first use, keyed by the
+        optimiser (a new phase creates a new optimiser) and the batch size."""
+        cache = fused.__dict__.setdefault("_graphs", {})
+        key = (id(optimizer), batch_size)
+        if key not in cache:
+            from ..fused import GraphedELBOStep
+            cache[key] = GraphedELBOStep(fused, optimizer, batch_size)
+        return cache[key]
+
+    @staticmethod
     def _update_model(model, elbo, optimizer, train_loader, eps=None):
         loss_iter = 0.0
         kl_iter = 0.0
         fused = BlackBoxMFDGPFitter._fused_step(model, elbo)
+        graphed = fused is not None and getattr(optimizer, "capturable", False) and eps is None
         for (x_batch, y_batch, fidelities) in train_loader:
+            if graphed and fused.applies(x_batch):
+                loss, kl = BlackBoxMFDGPFitter._graphed_step(fused, optimizer, x_batch.shape[0])(
+                    x_batch, y_batch, fidelities)            # forward, ELBO, backward AND the Adam update
+                loss_iter += loss.detach().clone()
+                kl_iter += kl.detach().clone()
+                continue
             if fused is not None and fused.applies(x_batch):
                 # forward, ELBO and backward in one enqueue; gradients are overwritten, so no zero_grad
                 loss, kl = fused(x_batch, y_batch, fidelities, eps=eps)
@@ -157,7 +178,7 @@ class BlackBoxMFDGPFitter():
             opts = []
             for h in handlers.values():
                 h.mfdgp.fix_variational_hypers(fix_variational_hypers)
-                opts.append(Adam([{'params': h.mfdgp.parameters()}], lr=lr))
+                opts.append(Adam([{'params': h.mfdgp.parameters()}], lr=lr, capturable=self.use_cuda_graph))
             for n, (h, optimizer) in enumerate(zip(handlers.values(), opts)):
                 for i in range(num_epochs):
                     loss_iter, kl_iter = func_update_model(h.mfdgp, h.elbo, optimizer, h.train_loader)

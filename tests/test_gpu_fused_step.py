@@ -223,3 +223,30 @@ def test_fused_acquisition_chain_matches_python_path_and_oracle():
         tol = max(parity_tol(mu_model)[0], parity_tol(mc_model)[0])
         assert float(val.max()) > 1e-3
         assert (val.cpu() - val_o).abs().max() < 100 * tol
+
+
+def test_cuda_graph_replay_matches_eager_steps():
+    """The captured (fused step + Adam) graph replays to the same parameters as the eager fused loop (Forrester-sized:
+    the launch-latency-bound regime of the reference's own examples)."""
+    from mobocmf_b200.fused import Adam, FusedELBOStep, GraphedELBOStep
+    from mobocmf_b200.mlls.variational_elbo_mf import VariationalELBOMF
+    L, S, B = 2, 1, 24
+    m1, x, y, fid, N = make_model(L=L, M=24, n_per=(14, 10), d=2)
+    m2 = copy.deepcopy(m1)
+    e1, e2 = VariationalELBOMF(m1, N, L), VariationalELBOMF(m2, N, L)
+    o1 = Adam([{"params": m1.parameters()}], lr=0.01, capturable=True)
+    o2 = Adam([{"params": m2.parameters()}], lr=0.01)
+    gstep = GraphedELBOStep(FusedELBOStep(m1, e1), o1, B, num_samples=S, static_eps=True)
+    estep = FusedELBOStep(m2, e2)
+    g = torch.Generator().manual_seed(3)
+    for it in range(6):
+        perm = torch.randperm(N, generator=g)[:B]
+        eps = [None] + [torch.randn(B * S, generator=g).double().to(DEV) for _ in range(1, L)]
+        xb, yb, fb = x[perm].to(DEV), y[perm].to(DEV), fid[perm].to(DEV)
+        l1, _ = gstep(xb, yb, fb, eps=eps)
+        l2, _ = estep(xb, yb, fb, eps=eps, num_samples=S)
+        o2.step()
+        assert relerr(l1, l2) < 1e-12, (it, relerr(l1, l2))
+    for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert relerr(a, b) < 1e-12, (n, relerr(a, b))
+    assert int(o1._step_dev) == 6
