@@ -254,8 +254,8 @@ def run_ours(args):
 
     # acquisition slice (C5-shaped): n candidates x S=25 samples through an (uncond, cond) pair at the top fidelity
     acq = None
-    if rank == 0 and not args.no_acq:
-        acq = bench_acq(model, dev, cfg)
+    if not args.no_acq:
+        acq = bench_acq(model, dev, cfg, world)
 
     if rank == 0:
         flops, f1 = step_flops(cfg)
@@ -308,7 +308,7 @@ def run_ours(args):
             out["kernel_ms_per_step"] = {k: round(v / nst, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}
         if acq:
             out["acq"] = acq
-        if not args.no_acq:
+        if not args.no_acq and world == 1:
             out["small_configs"] = bench_small_configs(dev)
         if not args.no_cpu and world == 1:      # reported on rank 0 at N = 1 only
             out["cpu_baseline"] = cpu_baseline(cfg, x, y, fid, model)
@@ -368,30 +368,81 @@ def bench_small_configs(dev, steps=200):
     return out
 
 
-def bench_acq(model, dev, cfg, n=20000, iters=3):
-    """JESMOC acquisition evals/s on a C5-shaped slice: n candidates x 25 samples, one (uncond, cond) MFDGP pair at
-    fidelity 2; one 'eval' = one candidate through _JES_MFDGP.forward (2 models x (1 + 25 + 25) rows)."""
+def bench_acq(model, dev, cfg, world, n=8192, K=6, P=16, iters=2):
+    """JESMOC acquisition sweep, BASELINE.json configs[4] (SURVEY.md section 8d "C5") on a slice: every rank evaluates
+    ITS n candidates (candidates shard across GPUs, no data-path collective) through the full coupled acquisition:
+    K = 6 black boxes (4 objectives + 2 constraints) x (1 unconditioned + P = 16 Pareto-conditioned) MFDGPs = 102 model
+    chains per candidate, each S = 25 samples through 3 layers (1 + 25 + 25 rows, M = 256):
+        acq(x) = 1/P sum_p sum_k 1/2 max(0, log v_u,k(x) - log v_c,k,p(x))
+    (mobocmf/acquisition_functions/JESMOC_MFDGP.py:38-52,125-135; P > 1 = average of P single-sample acquisitions,
+    SURVEY.md fact F5).  One 'eval' = one candidate through all 102 chains.  Models are random perturbations of the
+    bench model (timing does not depend on the parameter values)."""
     import copy
-    from mobocmf_b200.acquisition_functions.JESMOC_MFDGP import _JES_MFDGP
-    cond = copy.deepcopy(model)
-    with torch.no_grad():
-        for nme, p in cond.named_parameters():
-            if "chol_variational_covar" in nme:
-                p.mul_(0.7)
-    acq = _JES_MFDGP(cfg["L"] - 1, model, cond)
-    X = torch.rand(n, 1, cfg["d"], device=dev, dtype=torch.float64)
-    with torch.no_grad():
-        acq(X)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            acq(X)
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    return {"metric": "jesmoc_acq_evals_per_s", "value": n / (ms * 1e-3), "unit": "evals/s (1 black box, 1 Pareto "
-            "sample, forward)", "candidates": n, "ms": ms}
+    import torch.distributed as dist
+    from mobocmf_b200 import _lib
+    fidelity = cfg["L"] - 1
+    g = torch.Generator(device=dev).manual_seed(7)
+    unc, cond = [], []
+    for k in range(K):
+        u = copy.deepcopy(model)
+        with torch.no_grad():
+            for nme, p in u.named_parameters():
+                if "variational_mean" in nme:
+                    p.add_(0.05 * torch.randn(p.shape, generator=g, device=dev, dtype=p.dtype))
+        u.eval()
+        unc.append(u)
+        row = []
+        for pp in range(P):
+            c = copy.deepcopy(u)
+            with torch.no_grad():
+                for nme, p in c.named_parameters():
+                    if "chol_variational_covar" in nme:
+                        p.mul_(0.6 + 0.3 * (pp + 1) / P)
+            c.eval()
+            row.append(c)
+        cond.append(row)
+    X = torch.rand(n, cfg["d"], device=dev, dtype=torch.float64, generator=g)
+    lib = _lib.load()
+    out = torch.zeros(n, dtype=torch.float64, device=dev)
+
+    def sweep():
+        out.zero_()
+        with torch.no_grad():
+            for k in range(K):
+                _, vu = unc[k].predict_for_acquisition(X, fidelity)
+                unc[k].eval()
+                for pp in range(P):
+                    _, vc = cond[k][pp].predict_for_acquisition(X, fidelity)
+                    cond[k][pp].eval()
+                    _lib.check(lib.mobo_jes(_lib.ptr(vu), _lib.ptr(vc), n, 1, _lib.ptr(out), _lib.stream_ptr()),
+                               "mobo_jes")
+            out.div_(P)
+        return out
+
+    sweep()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        sweep()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    chains = K * (1 + P)
+    rows = chains * n * (1 + 2 * 25)
+    M, d = cfg["M"], cfg["d"]
+    flop = chains * n * ((2 * M * M + 2 * M + 3 * d * M) + 50 * (2 * M * M + 2 * M + 3 * (d + 1) * M))
+    return {"metric": "jesmoc_acq_evals_per_s", "value": world * n / (ms * 1e-3),
+            "unit": "candidates/s through the full coupled acquisition (6 black boxes x (1 + 16) MFDGPs, S=25, "
+                    "fidelity 2, forward)",
+            "candidates_per_gpu": n, "n_gpus": world, "ms_per_sweep": ms, "model_chains_per_candidate": chains,
+            "model_chain_evals_per_s": world * n * chains / (ms * 1e-3), "rows_per_s": world * rows / (ms * 1e-3),
+            "tflops_per_gpu": flop / (ms * 1e-3) / 1e12, "acq_mean": float(out.mean())}
 
 
 def cpu_baseline(cfg, x, y, fid, model, max_seconds=30.0):
