@@ -69,7 +69,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
@@ -100,6 +100,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg = dict(C4)
     x, y, fid = c4_data(cfg)
@@ -209,11 +211,14 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    for _ in range(max(args.warmup, 3)):
-        device_step()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.start()                   # sampled through warm-up and the timed region (a timed region of K steps
+    for _ in range(max(args.warmup, 3)):  # of 3 ms is shorter than one nvidia-smi call)
+        device_step()
+    if sampler:
+        while len(sampler.rows) < 2:      # at least two readings under load before the clock starts
+            device_step()
     l0 = _lib.launch_count()
     ms = timed(device_step, args.steps)
     launches = _lib.launch_count() - l0
