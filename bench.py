@@ -217,8 +217,10 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):  # of 3 ms is shorter than one nvidia-smi call)
         device_step()
     if sampler:
-        while len(sampler.rows) < 2:      # at least two readings under load before the clock starts
+        extra = 0
+        while len(sampler.rows) < 2 and extra < 300:   # two readings under load before the clock starts (bounded)
             device_step()
+            extra += 1
     l0 = _lib.launch_count()
     ms = timed(device_step, args.steps)
     launches = _lib.launch_count() - l0
