@@ -216,11 +216,8 @@ def run_ours(args):
         sampler.start()                   # sampled through warm-up and the timed region (a timed region of K steps
     for _ in range(max(args.warmup, 3)):  # of 3 ms is shorter than one nvidia-smi call)
         device_step()
-    if sampler:
-        extra = 0
-        while len(sampler.rows) < 2 and extra < 300:   # two readings under load before the clock starts (bounded)
-            device_step()
-            extra += 1
+    for _ in range(80):                   # ~0.25 s more under load on EVERY rank (the step holds a collective), so
+        device_step()                     # that the sampler has readings under load before the clock starts
     l0 = _lib.launch_count()
     ms = timed(device_step, args.steps)
     launches = _lib.launch_count() - l0
