@@ -166,3 +166,62 @@ def test_kl_zero_when_q_equals_prior():
         vd.variational_mean.zero_()
         vd.chol_variational_covar.copy_(Lp)
     assert abs(float(layer._kl_divergence())) < 1e-9
+
+
+def test_only_highest_fidelity_model_matches_oracle():
+    """use_only_highest_fidelity=True (mobocmf/models/mfdgp.py:78-89,189-190; layers/mfdgp_hidden_layer_only_hf.py):
+    per-layer inducing inputs (that fidelity's points only), layer >= 1 fed zeros, k_x1 / k_lin / k_f switched off and
+    frozen.  Not eligible for the fused step (inducing inputs are not shared): runs on the composable kernels."""
+    from mobocmf_b200.fused import FusedELBOStep
+    from mobocmf_b200.gp import settings
+    from mobocmf_b200.mlls.variational_elbo_mf import VariationalELBOMF
+    from mobocmf_b200.models.mfdgp import MFDGP
+    x, y, fid = synthetic_data([28, 14], 2, seed=8)
+    L, N = 2, x.shape[0]
+    torch.manual_seed(3)
+    model = MFDGP(x, y, fid, L, use_only_highest_fidelity=True, init_lengthscale=0.3)
+    model.double()
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.requires_grad and "chol_variational_covar" not in n:
+                p.add_(0.05 * torch.randn(p.shape, generator=g, dtype=p.dtype))
+    model.to(DEV)
+    assert model.hidden_layer_1.num_inducing == 14 and model.hidden_layer_0.num_inducing == 28
+    assert not FusedELBOStep.supported(model)[0]
+    elbo = VariationalELBOMF(model, N, L)
+    perm = torch.randperm(N, generator=g)
+    xb, yb, fb = x[perm], y[perm], fid[perm]
+    with settings.num_likelihood_samples(1):
+        out = model(xb.to(DEV))
+        res = elbo(out, yb.to(DEV).T, fb.to(DEV))
+    loss = -res[0]
+    loss.backward()
+
+    def fn(sd, lo, up, samples):
+        l, kl = O.elbo_step_loss(sd, L, up, xb, yb, fb, [None, None], N, noise_lower=lo, only_hf=True)
+        return l
+    sd, lo, up, samples = oracle_view(model)
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    for n in names:
+        sd[n].requires_grad_(True)
+    loss_o = fn(sd, lo, up, samples)
+    loss_o.backward()
+    tol, cond = parity_tol(model)
+    print("only-HF cond %.2e loss relerr %.2e" % (cond, relerr(loss, loss_o)))
+    assert relerr(loss, loss_o) < tol
+    for n, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        gp, go = p.grad, sd[n].grad
+        if "chol_variational_covar" in n:
+            gp, go = torch.tril(gp), torch.tril(go)
+        assert relerr(gp, go) < (1e3 * tol if cond < 1e5 else 1e-2), (n, relerr(gp, go))
+    # acquisition path of the only-HF model
+    model.eval()
+    X = torch.rand(9, 1, 2, generator=g, dtype=torch.float64)
+    with torch.no_grad():
+        mu, var = model.predict_for_acquisition(X.to(DEV), 1)
+    mu_o, var_o = O.predict_for_acquisition({k: v.detach() for k, v in sd.items()}, L, up, samples, X, 1,
+                                            only_hf=True, noise_lower=lo)
+    assert relerr(mu, mu_o) < tol and relerr(var, var_o) < 10 * tol
