@@ -10,6 +10,13 @@ class VariationalELBOMF(object):
         self.num_data = num_data
         self.num_fidelities = num_fidelities
 
+    def __getstate__(self):
+        # the fused-step binding (ctypes descriptors, device workspace, captured graphs) is rebuilt on demand and must
+        # not travel through copy.deepcopy / pickle (copy_uncond, mobocmf/util/blackbox_mfdgp_fitter.py:383)
+        state = self.__dict__.copy()
+        state.pop("_fused_step", None)
+        return state
+
     def forward(self, l_approximate_dist_f, target, fidelities, include_kl_term=True):
         assert target.shape[0] <= target.shape[1]   # the target must be (1, B)
         num_batch = target.shape[1]

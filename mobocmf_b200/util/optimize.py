@@ -27,7 +27,7 @@ def optimize_acqf(acq_function, bounds, q=1, num_restarts=5, raw_samples=200, op
         v = acq_function(Xc).double()
         loss = -v.sum()
         g, = torch.autograd.grad(loss, Xc)
-        return float(loss), g.detach().cpu().numpy().reshape(-1).astype(np.float64)
+        return float(loss.detach()), g.detach().cpu().numpy().reshape(-1).astype(np.float64)
 
     bnds = list(zip(lo.cpu().numpy().tolist(), hi.cpu().numpy().tolist())) * nb
     res = minimize(fun, x0, jac=True, method="L-BFGS-B", bounds=bnds,
