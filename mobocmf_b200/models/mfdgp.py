@@ -109,12 +109,29 @@ class MFDGP(nn.Module):
         if type_lengthscale == TL.ONES:
             return torch.ones(self.input_dims)
         elif type_lengthscale == TL.MEDIAN:
-            # includes quirk Q2: dists[(2,K) LongTensor] indexes ROWS, not the upper triangle (util/util.py:27-30)
-            dists_x_train = compute_dist(inputs)
-            return torch.sqrt(torch.median(dists_x_train[triu_indices(inputs.shape[0], 1)]))
+            return self.median_lengthscale(inputs)
         elif type_lengthscale == TL.CENTESIMAL:
             return 0.01 * np.ones(self.input_dims)
         raise ValueError("Wrong type of lengthscale.")
+
+    @staticmethod
+    def median_lengthscale(inputs, literal=False):
+        """``sqrt(median(dists[triu_indices(n, 1)]))`` of models/mfdgp.py:143-144 INCLUDING quirk Q2: the (2, K)
+        LongTensor indexes ROWS of the distance matrix (util/util.py:27-30), so the reference takes the median of a
+        (2, K, n) gather, n^2 (n - 1) values — unusable beyond a few hundred points.  Every row of the matrix occurs
+        exactly n - 1 times in that gather, so the multiset is n - 1 copies of the full matrix and torch.median's
+        lower-middle element is the order statistic ((n^2 (n-1) - 1) // 2) // (n - 1) of the n^2 matrix entries:
+        one k-th value over n^2 numbers (on the GPU when there is one), bit-identical to the literal formula."""
+        n = inputs.shape[0]
+        if literal or n < 2:
+            dists_x_train = compute_dist(inputs)
+            return torch.sqrt(torch.median(dists_x_train[triu_indices(n, 1)]))
+        x = inputs
+        if not x.is_cuda and torch.cuda.is_available() and n > 2048:
+            x = x.cuda()
+        flat = compute_dist(x).reshape(-1)
+        k = ((n * n * (n - 1) - 1) // 2) // (n - 1)
+        return torch.sqrt(torch.kthvalue(flat, k + 1).values).to(inputs.device)
 
     def train_mode(self):
         for i in range(self.num_hidden_layers):
@@ -284,8 +301,13 @@ class MFDGP(nn.Module):
         if self.num_inducing is not None:
             inducing_points = inducing_points[:self.num_inducing]
         xs, ys = x_train[sel, :], y_train[sel, :]
-        d = (xs ** 2).sum(1, keepdim=True) - 2.0 * xs.mm(inducing_points.T) + (inducing_points ** 2).sum(1)[None, :]
-        to_sel = torch.argmin(d, dim=0)
+        xs2 = (xs ** 2).sum(1, keepdim=True)
+        to_sel = []
+        for a in range(0, inducing_points.shape[0], 4096):        # chunked: the N_l x M distance block stays small
+            ip = inducing_points[a:a + 4096]
+            d = xs2 - 2.0 * xs.mm(ip.T) + (ip ** 2).sum(1)[None, :]
+            to_sel.append(torch.argmin(d, dim=0))
+        to_sel = torch.cat(to_sel)
         inducing_values = ys[to_sel, 0].to(torch.float32)
         if layer != 0:
             inducing_points = torch.cat((inducing_points, inducing_values[:, None]), 1)

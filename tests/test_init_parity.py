@@ -74,3 +74,21 @@ def test_state_dict_has_gpytorch_names_and_duplicates():
     import copy
     m2 = copy.deepcopy(model)
     m2.load_state_dict(model.state_dict())
+
+
+def test_median_lengthscale_order_statistic_equals_literal_formula():
+    """The scalable form of get_init_lengthscale(TL.MEDIAN) is bit-identical to the reference's literal row-gather
+    (quirk Q2) wherever the latter is computable."""
+    import torch
+    from mobocmf_b200.models.mfdgp import MFDGP
+    g = torch.Generator().manual_seed(0)
+    for n, d in [(2, 1), (3, 2), (12, 1), (16, 2), (37, 3), (60, 6)]:
+        x = torch.rand(n, d, generator=g, dtype=torch.float64)
+        fast = MFDGP.median_lengthscale(x)
+        literal = MFDGP.median_lengthscale(x, literal=True)
+        assert torch.equal(fast, literal), (n, d, float(fast), float(literal))
+    # the Forrester fixture's derived known answers (SURVEY.md section 4)
+    lf = torch.linspace(0, 1.0, 12, dtype=torch.float64)[:, None]
+    hf = torch.tensor([0.1, 0.3, 0.5, 0.7], dtype=torch.float64)[:, None]
+    assert abs(float(MFDGP.median_lengthscale(lf)) - 3.0 / 11.0) < 1e-12
+    assert abs(float(MFDGP.median_lengthscale(hf)) - 0.2) < 1e-12
