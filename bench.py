@@ -310,6 +310,9 @@ def run_ours(args):
                                "algorithmic_gflop_per_step": alg_per_step[top] / 1e9,
                                "share_of_step": ms_top / ms_step}
             out["kernel_ms_per_step"] = {k: round(v / nst, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}
+            out["kernel_ms_note"] = ("CUDA-event elapsed time per kernel; gemm / combine / kzz_bwd / white_vec / "
+                                     "dlq_extract / reduce_batch run on the step's side stream concurrently with the "
+                                     "row kernels, so their elapsed times include waiting and do not add up")
         if acq:
             out["acq"] = acq
         if not args.no_acq and world == 1:

@@ -256,6 +256,44 @@ int mobo_layer_rows_fwd(int kind, int d, int M, const double* Zx, const double* 
   return launch_row_fwd(a, (cudaStream_t)stream);
 }
 
+// the whitened statistics of one layer's backward (SYRK): A2, Ac, b into the operator-gradient buffer
+static int rows_bwd_stats(int MP, long long R, int training, const double* Tsave, const double* dmu,
+                          const double* dvar, const double* craw, const unsigned int* clamp_count, double* part_syrk,
+                          double* part_alpha, double* gops, cudaStream_t st) {
+  MOBO_TRY(launch_syrk(Tsave, dvar, craw, 0, MP, R, part_syrk, gops + ops_block(MP, OPS_W), clamp_count, dmu,
+                       part_alpha, gops + ops_alpha(MP), nullptr, st));
+  MOBO_TRY(launch_syrk(Tsave, dvar, craw, 1, MP, R, part_syrk, gops + ops_block(MP, OPS_H),
+                       training ? clamp_count : nullptr, nullptr, nullptr, nullptr,
+                       gops + ops_scal(MP) + SC_CLAMP, st));
+  return 0;
+}
+
+// product kernel + covariance-gradient kernel + the fixed-order reduction of the latter's per-CTA partials
+static int rows_bwd_main(RowArgs& a, int kind, int d, int M, long long R, double* dk, double* part, double* dtheta,
+                         double* dzf, cudaStream_t st) {
+  const int MP = a.MP;
+  const int grid = kgrad_grid(R);
+  a.dk = dk;
+  a.part_theta = part;
+  a.part_zf = part + (size_t)grid * MAX_THETA;
+  MOBO_TRY(launch_row_bwd(a, st));
+  if (a.want_param_grads && dtheta) {
+    MOBO_TRY(launch_reduce_partials(a.part_theta, grid, theta_size(kind, d), MAX_THETA, dtheta, 0, st));
+    if (kind == 1 && dzf) MOBO_TRY(launch_reduce_partials(a.part_zf, grid, M, MP, dzf, 0, st));
+  }
+  return 0;
+}
+
+static void fill_row_bwd_args(RowArgs& a, const double* dmu, const double* dvar, const double* craw,
+                              const double* Tsave, const double* Usave, int want_param_grads, double* df,
+                              double* dxrow) {
+  a.dmu = dmu; a.dvar = dvar; a.craw = const_cast<double*>(craw);
+  a.Tsave = const_cast<double*>(Tsave); a.Usave = const_cast<double*>(Usave);
+  a.df = df; a.dxrow = dxrow;
+  a.want_param_grads = want_param_grads; a.want_x_grads = dxrow != nullptr;
+  if (!a.want_param_grads && !a.want_x_grads) a.want_param_grads = 1;
+}
+
 int mobo_layer_rows_bwd(int kind, int d, int M, const double* Zx, const double* zf, const double* theta,
                         const double* ops, const double* x, int xrep, const double* mu_prev, const double* var_prev,
                         int prep, const double* eps, long long eps_mod, const double* f_direct, long long R,
@@ -267,31 +305,15 @@ int mobo_layer_rows_bwd(int kind, int d, int M, const double* Zx, const double* 
   RowArgs a;
   fill_row_args(a, kind, d, M, Zx, zf, theta, ops, x, xrep, mu_prev, var_prev, prep, eps, eps_mod, f_direct, R,
                 training);
+  fill_row_bwd_args(a, dmu, dvar, craw, Tsave, Usave, want_param_grads, df, dxrow);
   const int MP = a.MP;
-  a.dmu = dmu; a.dvar = dvar; a.craw = const_cast<double*>(craw);
-  a.Tsave = const_cast<double*>(Tsave); a.Usave = const_cast<double*>(Usave);
-  a.df = df; a.dxrow = dxrow;
-  a.want_param_grads = want_param_grads; a.want_x_grads = dxrow != nullptr;
-  if (!a.want_param_grads && !a.want_x_grads) a.want_param_grads = 1;
   const int grid = kgrad_grid(R);
-  a.dk = work;                                                   // [R][MP] scratch, first so that it stays aligned
-  double* part_theta = work + mobo_rows_save_doubles(M, R);
-  double* part_zf = part_theta + (size_t)grid * MAX_THETA;
-  double* part_syrk = part_zf + (size_t)grid * MP;
+  double* dk = work;                                             // [R][MP] scratch, first so that it stays aligned
+  double* part = work + mobo_rows_save_doubles(M, R);
+  double* part_syrk = part + (size_t)grid * (MAX_THETA + MP);
   double* part_alpha = part_syrk + syrk_part_doubles(MP, R);
-  a.part_theta = part_theta; a.part_zf = part_zf;
-  MOBO_TRY(launch_row_bwd(a, st));
-  if (a.want_param_grads && dtheta) {
-    MOBO_TRY(launch_reduce_partials(part_theta, grid, theta_size(kind, d), MAX_THETA, dtheta, 0, st));
-    if (kind == 1 && dzf) MOBO_TRY(launch_reduce_partials(part_zf, grid, M, MP, dzf, 0, st));
-  }
-  if (gops) {
-    MOBO_TRY(launch_syrk(Tsave, dvar, craw, 0, MP, R, part_syrk, gops + ops_block(MP, OPS_W), clamp_count, dmu,
-                         part_alpha, gops + ops_alpha(MP), nullptr, st));
-    MOBO_TRY(launch_syrk(Tsave, dvar, craw, 1, MP, R, part_syrk, gops + ops_block(MP, OPS_H),
-                         training ? clamp_count : nullptr, nullptr, nullptr, nullptr,
-                         gops + ops_scal(MP) + SC_CLAMP, st));
-  }
+  MOBO_TRY(rows_bwd_main(a, kind, d, M, R, dk, part, dtheta, dzf, st));
+  if (gops) MOBO_TRY(rows_bwd_stats(MP, R, training, Tsave, dmu, dvar, craw, clamp_count, part_syrk, part_alpha, gops, st));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -308,7 +330,7 @@ struct StepLayout {
       ell_part[ST_MAX_LAYERS];
   long long R[ST_MAX_LAYERS];
   int ell_blocks[ST_MAX_LAYERS];
-  size_t noise, clamp, rows_work, total;
+  size_t noise, clamp, rows_work, stats_work, total;
 };
 
 StepLayout step_layout(int L, int d, int M, int S, long long B) {
@@ -318,7 +340,7 @@ StepLayout step_layout(int L, int d, int M, int S, long long B) {
   const int MP = padded(M);
   y.noise = take(ST_MAX_LAYERS);
   y.clamp = take(ST_MAX_LAYERS);
-  size_t rows_work = 0;
+  size_t rows_work = 0, stats_work = 0;
   for (int l = 0; l < L; ++l) {
     const long long R = l == 0 ? B : B * (long long)S;
     y.R[l] = R;
@@ -335,15 +357,38 @@ StepLayout step_layout(int L, int d, int M, int S, long long B) {
     y.dLq_tmp[l] = take((size_t)M * M);
     y.pre_work[l] = take(mobo_precompute_bwd_work_doubles(M));
     y.ell_part[l] = take(2 * (size_t)y.ell_blocks[l]);
-    const size_t w = mobo_rows_bwd_work_doubles(M, R);
+    const size_t w = mobo_rows_save_doubles(M, R) + (size_t)256 * KG_CTAS_PER_SM * (MAX_THETA + MP) + 64;
     rows_work = w > rows_work ? w : rows_work;
+    const size_t sw = syrk_part_doubles(MP, R) + (size_t)syrk_nchunk(MP, R) * MP + 64;
+    stats_work = sw > stats_work ? sw : stats_work;
   }
   y.rows_work = take(rows_work);
+  y.stats_work = take(stats_work);
   y.total = off;
   (void)d;
   return y;
 }
 
+}  // namespace
+
+// Side stream of the fused step (one per device, created on first use): the SYRK statistics and the operator-chain
+// backward of layer l run there while the main stream already works on layer l - 1's row kernels; forked and joined
+// with events inside mobo_elbo_step, so the pattern is also valid under CUDA-graph capture.
+namespace {
+struct SideCtx { bool init = false; cudaStream_t s = nullptr; cudaEvent_t fork[ST_MAX_LAYERS]; cudaEvent_t join = nullptr; };
+SideCtx& side_ctx() {
+  static SideCtx ctx[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SideCtx& c = ctx[dev & 63];
+  if (!c.init) {
+    cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking);
+    for (int i = 0; i < ST_MAX_LAYERS; ++i) cudaEventCreateWithFlags(&c.fork[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming);
+    c.init = true;
+  }
+  return c;
+}
 }  // namespace
 
 size_t mobo_elbo_step_workspace_doubles(int L, int d, int M, int S, long long B) {
@@ -403,7 +448,10 @@ int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
                                  ws + y.mu[l], ws + y.var[l], ws + y.craw[l], clamp + l, ws + y.Ts[l], ws + y.Us[l],
                                  stream));
   }
-  // 4. ELBO terms and backward row passes, high -> low fidelity
+  // 4. ELBO terms and backward row passes, high -> low fidelity.  Per layer the main stream runs the SYRK statistics,
+  //    the product and the covariance-gradient kernels; that layer's operator-chain backward (a dozen latency-bound
+  //    M x M launches) runs on the side stream, hidden behind the row kernels.
+  SideCtx& sc = side_ctx();
   for (int l = L - 1; l >= 0; --l) {
     const long long R = y.R[l];
     EllArgs e;
@@ -414,16 +462,26 @@ int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
     e.prep_next = l + 1 < L ? (int)(y.R[l + 1] / R) : 1;
     e.dmu = ws + y.dmu[l]; e.dvar = ws + y.dvar[l]; e.part = ws + y.ell_part[l];
     MOBO_LAUNCH("ell_kernel", st, ell_kernel<<<y.ell_blocks[l], ELL_THREADS, 0, st>>>(e));
-    MOBO_TRY(mobo_layer_rows_bwd(kinds[l], d, M, Zx[l], zf[l], theta[l], ops[l], D->x, l == 0 ? 1 : S,
-                                 l == 0 ? nullptr : ws + y.mu[l - 1], l == 0 ? nullptr : ws + y.var[l - 1],
-                                 l == 0 ? 1 : (int)(R / y.R[l - 1]), D->layer[l].eps, R, nullptr, R, 1,
-                                 ws + y.dmu[l], ws + y.dvar[l], ws + y.craw[l], clamp + l, ws + y.Ts[l],
-                                 ws + y.Us[l], 1, ws + y.df[l], nullptr, ws + y.dtheta_rows[l],
-                                 l == 0 ? nullptr : ws + y.dzf_rows[l], ws + y.gops[l], ws + y.rows_work, stream));
+    // SYRK statistics on the main stream (DMMA-bound like the row kernels: running them side by side only made both
+    // slower); the latency-bound operator-chain backward of this layer goes to the side stream
+    MOBO_TRY(rows_bwd_stats(MP, R, 1, ws + y.Ts[l], ws + y.dmu[l], ws + y.dvar[l], ws + y.craw[l], clamp + l,
+                            ws + y.stats_work, ws + y.stats_work + syrk_part_doubles(MP, R), ws + y.gops[l], st));
+    if (cudaEventRecord(sc.fork[l], st) != cudaSuccess || cudaStreamWaitEvent(sc.s, sc.fork[l], 0) != cudaSuccess) return -1;
+    MOBO_TRY(mobo_model_precompute_bwd(1, kinds + l, d, M, Zx + l, zf + l, theta + l, m + l, Lq + l, cops + l, gops + l,
+                                       pre_work + l, dtheta_pre + l, dzf_pre + l, dm_pre + l, dLq + l, (void*)sc.s));
+    // main stream: dk = W^T dt and the covariance gradient
+    RowArgs a;
+    fill_row_args(a, kinds[l], d, M, Zx[l], zf[l], theta[l], ops[l], D->x, l == 0 ? 1 : S,
+                  l == 0 ? nullptr : ws + y.mu[l - 1], l == 0 ? nullptr : ws + y.var[l - 1],
+                  l == 0 ? 1 : (int)(R / y.R[l - 1]), D->layer[l].eps, R, nullptr, R, 1);
+    fill_row_bwd_args(a, ws + y.dmu[l], ws + y.dvar[l], ws + y.craw[l], ws + y.Ts[l], ws + y.Us[l], 1, ws + y.df[l],
+                      nullptr);
+    a.clamp_count = clamp + l;
+    MOBO_TRY(rows_bwd_main(a, kinds[l], d, M, R, ws + y.rows_work, ws + y.rows_work + mobo_rows_save_doubles(M, R),
+                           ws + y.dtheta_rows[l], l == 0 ? nullptr : ws + y.dzf_rows[l], st));
   }
-  // 5. backward of the operator chains
-  MOBO_TRY(mobo_model_precompute_bwd(L, kinds, d, M, Zx, zf, theta, m, Lq, cops, gops, pre_work, dtheta_pre, dzf_pre,
-                                     dm_pre, dLq, stream));
+  // 5. join: the gradient assembly needs both streams' results
+  if (cudaEventRecord(sc.join, sc.s) != cudaSuccess || cudaStreamWaitEvent(st, sc.join, 0) != cudaSuccess) return -1;
   // 6. gradient assembly
   {
     FinishArgs a;
