@@ -248,6 +248,7 @@ def run_ours(args):
     nprof = min(args.steps, 5)
     if rank == 0:
         _lib.profile_enable(True)
+        _lib.load().mobo_step_side_stream(0)   # serialise the step's side stream so that per-kernel times are clean
     for _ in range(nprof):            # every rank steps (the step contains the gradient all-reduce); rank 0 records
         device_step()
     torch.cuda.synchronize()
@@ -255,6 +256,7 @@ def run_ours(args):
         for name, t in _lib.profile_collect():
             prof.setdefault(name, []).append(t)
         _lib.profile_enable(False)
+        _lib.load().mobo_step_side_stream(1)
 
     # acquisition slice (C5-shaped): n candidates x S=25 samples through an (uncond, cond) pair at the top fidelity
     acq = None
@@ -310,15 +312,15 @@ def run_ours(args):
                                "algorithmic_gflop_per_step": alg_per_step[top] / 1e9,
                                "share_of_step": ms_top / ms_step}
             out["kernel_ms_per_step"] = {k: round(v / nst, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}
-            out["kernel_ms_note"] = ("CUDA-event elapsed time per kernel; gemm / combine / kzz_bwd / white_vec / "
-                                     "dlq_extract / reduce_batch run on the step's side stream concurrently with the "
-                                     "row kernels, so their elapsed times include waiting and do not add up")
+            out["kernel_ms_note"] = ("CUDA-event time per kernel over %d extra steps run with the step's side stream "
+                                     "serialised (mobo_step_side_stream(0)); in the timed region the operator-chain "
+                                     "backward overlaps the row kernels, so ms_per_step is below the sum" % nst)
         if acq:
             out["acq"] = acq
         if not args.no_acq and world == 1:
             out["small_configs"] = bench_small_configs(dev)
         if not args.no_cpu and world == 1:      # reported on rank 0 at N = 1 only
-            out["cpu_baseline"] = cpu_baseline(cfg, x, y, fid, model)
+            out["cpu_baseline"] = cpu_baseline(cfg, x, y, fid, model, max_seconds=25.0, steps=10, warmup=2)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -332,12 +334,33 @@ def bench_small_configs(dev, steps=200):
     from mobocmf_b200.fused import Adam, FusedELBOStep, GraphedELBOStep
     from mobocmf_b200.mlls.variational_elbo_mf import VariationalELBOMF
     from mobocmf_b200.models.mfdgp import MFDGP
-    from tests.helpers import forrester_data, synthetic_data
+    import numpy as np
+
+    def forrester_data():
+        """Deterministic data of examples/example_acquisition_mfdgp_forrester/...py:51-104 (config C2)."""
+        mf1 = lambda t: ((6 * t - 2) ** 2) * np.sin(12 * t - 4)
+        mf0 = lambda t: 0.5 * mf1(t) + 10 * (t - 0.5) + 5
+        x0, x1 = np.linspace(0, 1.0, 12).reshape(12, 1), np.array([0.1, 0.3, 0.5, 0.7]).reshape(4, 1)
+        y0, y1 = mf0(x0), mf1(x1)
+        mean, std = np.mean(np.vstack((y1, y0))), np.std(np.vstack((y1, y0)))
+        yy = torch.cat((torch.from_numpy((y1 - mean) / std), torch.from_numpy((y0 - mean) / std)), 0).double()
+        xx = torch.cat((torch.from_numpy(x1), torch.from_numpy(x0)), 0).double()
+        ff = torch.cat((torch.ones(4).double(), torch.zeros(12).double()))[:, None]
+        return xx, yy, ff
+
+    def synthetic_data(n_per_fid, d, seed=0):
+        gg = torch.Generator().manual_seed(seed)
+        xs, ys, fs = [], [], []
+        for l, n in enumerate(n_per_fid):
+            xx = torch.rand(n, d, generator=gg, dtype=torch.float64)
+            y0 = torch.sin(2 * math.pi * xx).sum(1) / math.sqrt(d)
+            yl = y0 if l == 0 else 0.8 * y0 + 0.2 * torch.cos(math.pi * xx.sum(1))
+            xs.append(xx); ys.append(yl[:, None]); fs.append(torch.full((n, 1), float(l), dtype=torch.float64))
+        return torch.cat(xs), torch.cat(ys), torch.cat(fs)
     out = {}
     for name in ("C2_forrester_N16", "C1C3_sized_N75"):
         if name.startswith("C2"):
-            x, ys, fid = forrester_data()
-            y = ys["obj1"]
+            x, y, fid = forrester_data()
         else:
             x, y, fid = synthetic_data([50, 25], 2, seed=4)
         N = x.shape[0]
@@ -452,9 +475,10 @@ def bench_acq(model, dev, cfg, world, n=8192, K=6, P=16, iters=2):
             "tflops_per_gpu": flop / (ms * 1e-3) / 1e12, "acq_mean": float(out.mean())}
 
 
-def cpu_baseline(cfg, x, y, fid, model, max_seconds=30.0):
+def cpu_baseline(cfg, x, y, fid, model, max_seconds=30.0, steps=3, warmup=1):
     """The oracle's tiled S-sample ELBO step (forward + autograd backward + Adam) on the host cores, on a bounded
-    sample of the same workload: same model / B / M, S reduced to S_cpu and scaled by rows."""
+    sample of the same workload: same model / B / M, S reduced to S_cpu and scaled by rows.  This leg (and
+    ``--impl reference``) is the only place where bench.py executes ``oracle/``."""
     from oracle import mfdgp_oracle as O
     from tests.helpers import oracle_view
     torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
@@ -467,7 +491,7 @@ def cpu_baseline(cfg, x, y, fid, model, max_seconds=30.0):
     opt = torch.optim.Adam([sd[n] for n in names], lr=0.001)
     times = []
     t_start = time.time()
-    for it in range(4):
+    for it in range(warmup + steps):
         idx = torch.randint(0, N, (B,), generator=g)
         eps = [None] + [torch.randn(B * S_cpu, generator=g).double() for _ in range(1, L)]
         t0 = time.time()
@@ -475,16 +499,17 @@ def cpu_baseline(cfg, x, y, fid, model, max_seconds=30.0):
         loss, _ = O.elbo_step_loss_tiled(sd, L, up, x[idx], y[idx], fid[idx], eps, N, S_cpu, noise_lower=lo)
         loss.backward()
         opt.step()
-        times.append(time.time() - t0)
-        if time.time() - t_start > max_seconds:
+        if it >= warmup:
+            times.append(time.time() - t0)
+        if time.time() - t_start > max_seconds and times:
             break
-    t = min(times[1:]) if len(times) > 1 else times[0]
+    t = sum(times) / len(times)
     rows_full = B + (L - 1) * B * cfg["S"]
     rows_cpu = B + (L - 1) * B * S_cpu
     t_full = t * rows_full / rows_cpu
     return {"value": 1.0 / t_full, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "oracle tiled ELBO step (fwd+autograd bwd+Adam), B=1024, M=256, S=%d instead of 64 "
-                      "(%.2f s/step), scaled by rows x%.2f" % (S_cpu, t, rows_full / rows_cpu)}
+            "sample": "oracle tiled ELBO step (fwd + autograd bwd + Adam), B=1024, M=256, S=%d of the 64 samples "
+                      "(mean %.3f s over %d steps), scaled by rows x%.2f" % (S_cpu, t, len(times), rows_full / rows_cpu)}
 
 
 def run_reference(args):
@@ -500,7 +525,7 @@ def run_reference(args):
     torch.manual_seed(cfg["seed"])
     model = MFDGP(x, y, fid, cfg["L"], num_inducing=cfg["M"], init_lengthscale=cfg["lengthscale"])
     model.double()
-    cb = cpu_baseline(cfg, x, y, fid, model, max_seconds=120.0)
+    cb = cpu_baseline(cfg, x, y, fid, model, max_seconds=150.0, steps=max(1, args.steps), warmup=max(1, args.warmup))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     out = {"impl": "reference", "metric": "mfdgp_elbo_steps_per_s", "value": cb["value"], "unit": "steps/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],

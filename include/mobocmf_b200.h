@@ -147,6 +147,9 @@ typedef struct mobo_step_desc {
 } mobo_step_desc;
 
 size_t mobo_elbo_step_workspace_doubles(int L, int d, int M, int S, long long B);
+/* mobo_elbo_step runs each layer's operator-chain backward on an internal side stream behind the row kernels
+ * (default).  0 serialises everything on the caller's stream (used by bench.py's per-kernel timing leg). */
+void mobo_step_side_stream(int on);
 int mobo_elbo_step(const mobo_step_desc* desc, void* stream);
 
 /* torch.optim.Adam update (mobocmf/util/blackbox_mfdgp_fitter.py:126,132,259; defaults betas (0.9, 0.999),

@@ -327,10 +327,10 @@ struct StepLayout {
       craw[ST_MAX_LAYERS], dmu[ST_MAX_LAYERS], dvar[ST_MAX_LAYERS], df[ST_MAX_LAYERS], Ts[ST_MAX_LAYERS],
       Us[ST_MAX_LAYERS], dtheta_rows[ST_MAX_LAYERS], dtheta_pre[ST_MAX_LAYERS], dzf_rows[ST_MAX_LAYERS],
       dzf_pre[ST_MAX_LAYERS], dm_pre[ST_MAX_LAYERS], dLq_tmp[ST_MAX_LAYERS], pre_work[ST_MAX_LAYERS],
-      ell_part[ST_MAX_LAYERS];
+      ell_part[ST_MAX_LAYERS], stats0[ST_MAX_LAYERS], stats1[ST_MAX_LAYERS], stats_alpha[ST_MAX_LAYERS];
   long long R[ST_MAX_LAYERS];
   int ell_blocks[ST_MAX_LAYERS];
-  size_t noise, clamp, rows_work, stats_work, total;
+  size_t noise, clamp, rows_work, total;
 };
 
 StepLayout step_layout(int L, int d, int M, int S, long long B) {
@@ -340,7 +340,7 @@ StepLayout step_layout(int L, int d, int M, int S, long long B) {
   const int MP = padded(M);
   y.noise = take(ST_MAX_LAYERS);
   y.clamp = take(ST_MAX_LAYERS);
-  size_t rows_work = 0, stats_work = 0;
+  size_t rows_work = 0;
   for (int l = 0; l < L; ++l) {
     const long long R = l == 0 ? B : B * (long long)S;
     y.R[l] = R;
@@ -359,11 +359,13 @@ StepLayout step_layout(int L, int d, int M, int S, long long B) {
     y.ell_part[l] = take(2 * (size_t)y.ell_blocks[l]);
     const size_t w = mobo_rows_save_doubles(M, R) + (size_t)256 * KG_CTAS_PER_SM * (MAX_THETA + MP) + 64;
     rows_work = w > rows_work ? w : rows_work;
-    const size_t sw = syrk_part_doubles(MP, R) + (size_t)syrk_nchunk(MP, R) * MP + 64;
-    stats_work = sw > stats_work ? sw : stats_work;
+    // SYRK partials per layer and per weight set: their fold runs on the side stream while the main stream is already
+    // in the next layer's SYRK
+    y.stats0[l] = take(syrk_part_doubles(MP, R));
+    y.stats1[l] = take(syrk_part_doubles(MP, R));
+    y.stats_alpha[l] = take((size_t)syrk_nchunk(MP, R) * MP + 64);
   }
   y.rows_work = take(rows_work);
-  y.stats_work = take(stats_work);
   y.total = off;
   (void)d;
   return y;
@@ -390,6 +392,9 @@ SideCtx& side_ctx() {
   return c;
 }
 }  // namespace
+
+static bool g_side_stream_on = true;
+void mobo_step_side_stream(int on) { g_side_stream_on = on != 0; }
 
 size_t mobo_elbo_step_workspace_doubles(int L, int d, int M, int S, long long B) {
   if (L < 1 || L > ST_MAX_LAYERS) return 0;
@@ -452,6 +457,8 @@ int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
   //    the product and the covariance-gradient kernels; that layer's operator-chain backward (a dozen latency-bound
   //    M x M launches) runs on the side stream, hidden behind the row kernels.
   SideCtx& sc = side_ctx();
+  const bool fork = g_side_stream_on;
+  cudaStream_t ss = fork ? sc.s : st;
   for (int l = L - 1; l >= 0; --l) {
     const long long R = y.R[l];
     EllArgs e;
@@ -462,13 +469,22 @@ int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
     e.prep_next = l + 1 < L ? (int)(y.R[l + 1] / R) : 1;
     e.dmu = ws + y.dmu[l]; e.dvar = ws + y.dvar[l]; e.part = ws + y.ell_part[l];
     MOBO_LAUNCH("ell_kernel", st, ell_kernel<<<y.ell_blocks[l], ELL_THREADS, 0, st>>>(e));
-    // SYRK statistics on the main stream (DMMA-bound like the row kernels: running them side by side only made both
-    // slower); the latency-bound operator-chain backward of this layer goes to the side stream
-    MOBO_TRY(rows_bwd_stats(MP, R, 1, ws + y.Ts[l], ws + y.dmu[l], ws + y.dvar[l], ws + y.craw[l], clamp + l,
-                            ws + y.stats_work, ws + y.stats_work + syrk_part_doubles(MP, R), ws + y.gops[l], st));
-    if (cudaEventRecord(sc.fork[l], st) != cudaSuccess || cudaStreamWaitEvent(sc.s, sc.fork[l], 0) != cudaSuccess) return -1;
+    // SYRK proper on the main stream (DMMA-bound like the row kernels: running them side by side only made both
+    // slower); the fold of its partials and the latency-bound operator-chain backward of this layer go to the side
+    // stream
+    double* gl = ws + y.gops[l];
+    MOBO_TRY(launch_syrk_main(ws + y.Ts[l], ws + y.dvar[l], ws + y.craw[l], 0, MP, R, ws + y.stats0[l], clamp + l,
+                              ws + y.dmu[l], ws + y.stats_alpha[l], st));
+    MOBO_TRY(launch_syrk_main(ws + y.Ts[l], ws + y.dvar[l], ws + y.craw[l], 1, MP, R, ws + y.stats1[l], clamp + l,
+                              nullptr, nullptr, st));
+    if (fork && (cudaEventRecord(sc.fork[l], st) != cudaSuccess || cudaStreamWaitEvent(ss, sc.fork[l], 0) != cudaSuccess))
+      return -1;
+    MOBO_TRY(launch_syrk_reduce(0, MP, R, ws + y.stats0[l], gl + ops_block(MP, OPS_W), clamp + l, ws + y.stats_alpha[l],
+                                gl + ops_alpha(MP), nullptr, ss));
+    MOBO_TRY(launch_syrk_reduce(1, MP, R, ws + y.stats1[l], gl + ops_block(MP, OPS_H), clamp + l, nullptr, nullptr,
+                                gl + ops_scal(MP) + SC_CLAMP, ss));
     MOBO_TRY(mobo_model_precompute_bwd(1, kinds + l, d, M, Zx + l, zf + l, theta + l, m + l, Lq + l, cops + l, gops + l,
-                                       pre_work + l, dtheta_pre + l, dzf_pre + l, dm_pre + l, dLq + l, (void*)sc.s));
+                                       pre_work + l, dtheta_pre + l, dzf_pre + l, dm_pre + l, dLq + l, (void*)ss));
     // main stream: dk = W^T dt and the covariance gradient
     RowArgs a;
     fill_row_args(a, kinds[l], d, M, Zx[l], zf[l], theta[l], ops[l], D->x, l == 0 ? 1 : S,
@@ -481,7 +497,7 @@ int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
                            ws + y.dtheta_rows[l], l == 0 ? nullptr : ws + y.dzf_rows[l], st));
   }
   // 5. join: the gradient assembly needs both streams' results
-  if (cudaEventRecord(sc.join, sc.s) != cudaSuccess || cudaStreamWaitEvent(st, sc.join, 0) != cudaSuccess) return -1;
+  if (fork && (cudaEventRecord(sc.join, ss) != cudaSuccess || cudaStreamWaitEvent(st, sc.join, 0) != cudaSuccess)) return -1;
   // 6. gradient assembly
   {
     FinishArgs a;

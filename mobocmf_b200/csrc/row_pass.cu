@@ -1064,9 +1064,10 @@ int syrk_nchunk(int MP, long long R) {
 size_t syrk_part_doubles(int MP, long long R) { return (size_t)syrk_nblocks(MP) * syrk_nchunk(MP, R) * 1024; }
 
 // part: syrk_part_doubles(MP, R) doubles of scratch; part_alpha: nchunk * MP doubles (which == 0 only)
-int launch_syrk(const double* K, const double* dvar, const double* craw, int which, int MP, long long R,
-                double* part, double* A, const unsigned int* clamp_count, const double* dmu, double* part_alpha,
-                double* dalpha, double* clamp_flag_out, cudaStream_t st) {
+// the SYRK proper (DMMA-bound): per-chunk partial blocks into `part`, partial b into part_alpha (which == 0)
+int launch_syrk_main(const double* K, const double* dvar, const double* craw, int which, int MP, long long R,
+                     double* part, const unsigned int* clamp_count, const double* dmu, double* part_alpha,
+                     cudaStream_t st) {
   const int nc = syrk_nchunk(MP, R);
   const size_t smem = SY_STAGES * syrk_stage_doubles(MP) * sizeof(double);
   static bool attr_done = false;
@@ -1078,10 +1079,26 @@ int launch_syrk(const double* K, const double* dvar, const double* craw, int whi
   dim3 grid(syrk_ngroups(MP), nc);
   MOBO_LAUNCH("syrk_kernel", st, syrk_kernel<<<grid, SY_THREADS, smem, st>>>(K, dvar, craw, which, MP, R, nc, part, clamp_count,
                                            which == 0 ? dmu : nullptr, which == 0 ? part_alpha : nullptr));
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// fixed-order fold of the partials into the symmetric matrix A (and b), latency-bound: may run on another stream
+int launch_syrk_reduce(int which, int MP, long long R, const double* part, double* A,
+                       const unsigned int* clamp_count, const double* part_alpha, double* dalpha,
+                       double* clamp_flag_out, cudaStream_t st) {
+  const int nc = syrk_nchunk(MP, R);
   MOBO_LAUNCH("syrk_reduce_kernel", st, syrk_reduce_kernel<<<(MP * MP + 255) / 256, 256, 0, st>>>(part, nc, MP, A, which, clamp_count, clamp_flag_out));
   if (which == 0 && part_alpha && dalpha)
     MOBO_LAUNCH("reduce_partials_kernel", st, reduce_partials_kernel<<<(MP + 3) / 4, 128, 0, st>>>(part_alpha, nc, MP, MP, dalpha, 0));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_syrk(const double* K, const double* dvar, const double* craw, int which, int MP, long long R,
+                double* part, double* A, const unsigned int* clamp_count, const double* dmu, double* part_alpha,
+                double* dalpha, double* clamp_flag_out, cudaStream_t st) {
+  const int e = launch_syrk_main(K, dvar, craw, which, MP, R, part, clamp_count, dmu, part_alpha, st);
+  if (e) return e;
+  return launch_syrk_reduce(which, MP, R, part, A, clamp_count, part_alpha, dalpha, clamp_flag_out, st);
 }
 
 }  // namespace mobo
