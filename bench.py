@@ -241,7 +241,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms_e2e)
-    assert all(v is not None and math.isfinite(v) for v in e2e_losses[-args.steps:])
+    e2e_finite = all(v is not None and math.isfinite(v) for v in e2e_losses[-args.steps:])
 
     # per-kernel CUDA-event timing of a few extra steps (launch stream = torch's current stream)
     prof = {}
@@ -276,6 +276,7 @@ def run_ours(args):
                        "cache": "per-step working set (3 x 134 MB saved tiles per upper layer) exceeds L2"},
             "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": "steps/s",
                     "h2d_bytes_per_step": B * (cfg["d"] + 2) * 8, "d2h_bytes_per_step": 8,
+                    "losses_finite": e2e_finite, "last_loss": e2e_losses[-1],
                     "note": "host minibatch -> pinned H2D -> fused step + Adam -> loss D2H, every step; the loss of "
                             "step i is read while step i+1 is enqueued"},
             "gpu_launches": int(launches),
