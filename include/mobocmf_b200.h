@@ -13,8 +13,8 @@
  *           theta = [a1, v_lin, a_f, l_f, a2, l1_0 .. l1_{d-1}, l2_0 .. l2_{d-1}]
  *   theta holds CONSTRAINED values (softplus already applied); d = number of x columns (without f).
  *   MP = M rounded up to a multiple of 32.  An "operator buffer" is mobo_ops_doubles(M) doubles laid out as
- *   [L | W | WT | H | HT | P | LQ] (seven MP x MP row-major blocks), beta[MP], alpha[MP], scal[16], rowstat[4 MP],
- *   flags[128]
+ *   [L | W | WT | H | HT | P | LQ] (seven MP x MP row-major blocks), [WF | HTF | HF | WTF] (W, HT, H, WT again in the
+ *   DMMA A-fragment order the row kernels stream them in), beta[MP], alpha[MP], scal[16], rowstat[4 MP], flags[128]
  *   (scal[0] = KL, scal[5] = Cholesky status: 0 ok, 1 not positive definite).
  *   The GRADIENT of an operator buffer uses the same layout and, by convention, carries only
  *   block W: A2 = sum_r dvar_r t_r t_r^T (t = W k, whitened), block H: the same sum over clamped rows,

@@ -41,13 +41,23 @@ constexpr int kMaxD = 8;               // max number of x columns (ARD dims) han
 constexpr double kMinVariance = 1e-10; // gpytorch settings.min_variance (fp64), quirk Q9
 
 // ---- operator buffer layout (doubles), one per (model, layer); MP = M rounded up to a multiple of 32 ----
-// [L | W | WT | H | HT | P | LQ]  seven MP x MP row-major blocks, then beta[MP], alpha[MP], scal[16], rowstat[4 MP],
-// flags[128]
+// [L | W | WT | H | HT | P | LQ | WF | HTF | HF | WTF]  eleven MP x MP blocks, then beta[MP], alpha[MP], scal[16],
+// rowstat[4 MP], flags[128]
 //   L = chol(K_zz + jitter I), W = L^-1, WT = W^T, H = W tril(L_q), HT = H^T, P = K_zz + jitter I, LQ = tril(L_q)
+//   (row-major), and WF / HTF / HF / WTF = W / HT / H / WT again in DMMA A-fragment order (frag_offset below), the
+//   form the row kernels stream them in: one 16-byte load per lane and k-step, 512 contiguous bytes per warp.
+//   Only the 32 x 32 blocks of the populated triangle (diagonal blocks included) of the fragment copies are written.
 // The GRADIENT buffer of an operator buffer has the same layout and carries, by convention of this library,
 //   block OPS_W: A2 = sum_r dvar_r t_r t_r^T (t = W k),  block OPS_H: Ac = same over clamped rows only,
 //   alpha slot: b = sum_r dmu_r t_r,  scal[SC_KL]: d loss / d KL, scal[SC_CLAMP]: #clamped rows;  rest ignored.
-enum OpsBlock { OPS_L = 0, OPS_W = 1, OPS_WT = 2, OPS_H = 3, OPS_HT = 4, OPS_P = 5, OPS_LQ = 6, OPS_NBLOCKS = 7 };
+enum OpsBlock { OPS_L = 0, OPS_W = 1, OPS_WT = 2, OPS_H = 3, OPS_HT = 4, OPS_P = 5, OPS_LQ = 6,
+                OPS_WF = 7, OPS_HTF = 8, OPS_HF = 9, OPS_WTF = 10, OPS_NBLOCKS = 11 };
+// A-fragment order of mma.sync.m8n8k4.f64 for 16-row slabs: element (i, k) of an MP x MP operator lives at
+//   ((i / 16) * (MP / 4) + k / 4) * 64 + 2 * lane + (i / 8) % 2,   lane = 4 * (i % 8) + k % 4
+// so lane `lane` of a warp working on slab s reads the double2 {A[16 s + g][k0 + t], A[16 s + 8 + g][k0 + t]}.
+__host__ __device__ inline size_t frag_offset(int MP, int i, int k) {
+  return ((size_t)(i >> 4) * (MP >> 2) + (k >> 2)) * 64 + 2 * (4 * (i & 7) + (k & 3)) + ((i >> 3) & 1);
+}
 // scal[SC_CLAMP] is meaningful in the GRADIENT buffer: number of clamped rows behind block OPS_H (0 -> Ac == 0)
 enum OpsScal { SC_KL = 0, SC_LOGDET_P = 1, SC_LOGDET_Q = 2, SC_BETA2 = 3, SC_H2 = 4, SC_STATUS = 5, SC_CLAMP = 6,
                SC_COUNTER = 8 };

@@ -67,6 +67,19 @@ __device__ __forceinline__ void oc_store(double* __restrict__ dst, int ld, const
 #pragma unroll
   for (int q = 0; q < 8; ++q) dst[(size_t)r * ld + c0 + q] = transpose ? src[(c0 + q) * OC_LD + r] : src[r * OC_LD + c0 + q];
 }
+// shared [32][OC_LD] (optionally read transposed) -> block (rb, cb) of a fragment-order operator copy (common.cuh
+// frag_offset): the block is 2 slabs x 8 k-steps of 64 contiguous doubles
+__device__ __forceinline__ void oc_store_frag(double* __restrict__ frag, int MP, int rb, int cb,
+                                              const double* __restrict__ src, bool transpose) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int e = threadIdx.x + OC_THREADS * q;
+    const int ib = e & 1, lane = (e >> 1) & 31, kq = (e >> 6) & 7, sl = e >> 9;
+    const int r = 16 * sl + 8 * ib + (lane >> 2), c = 4 * kq + (lane & 3);
+    frag[((size_t)(2 * rb + sl) * (MP >> 2) + 8 * cb + kq) * 64 + (e & 63)] =
+        transpose ? src[c * OC_LD + r] : src[r * OC_LD + c];
+  }
+}
 __device__ __forceinline__ void oc_zero_block(double* __restrict__ dst, int ld) {
   const int r = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 8;
 #pragma unroll
@@ -310,6 +323,11 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
   oc_store(blk(Hg, bi, bj), MP, Cbuf, false);
   oc_store(blk(HTg, bj, bi), MP, Cbuf, true);
   if (!diag) { oc_zero_block(blk(Hg, bj, bi), MP); oc_zero_block(blk(HTg, bi, bj), MP); }
+  // fragment-order copies for the row kernels (nobody in this launch waits for them): Dbuf = W_ij, Cbuf = H_ij
+  oc_store_frag(ops + ops_block(MP, OPS_WF), MP, bi, bj, Dbuf, false);
+  oc_store_frag(ops + ops_block(MP, OPS_WTF), MP, bj, bi, Dbuf, true);
+  oc_store_frag(ops + ops_block(MP, OPS_HF), MP, bi, bj, Cbuf, false);
+  oc_store_frag(ops + ops_block(MP, OPS_HTF), MP, bj, bi, Cbuf, true);
 
   OC_TICK(5);
   // ---- per-CTA pieces of the KL: |H_ij|_F^2; diagonal CTAs add beta_i, |beta_i|^2 and the log-determinants ----

@@ -51,7 +51,7 @@ struct RowArgs {
   double* craw;            // optional: k_xx - |t|^2 before the clamp (mask for the backward)
   unsigned int* clamp_count; // optional: number of rows whose k_xx - |t|^2 was clamped
   double* Tsave;           // optional row-major [R][MP]: whitened rows t = W k
-  double* Usave;           // optional fragment-major [tile][warp][32][32]: u = H^T t
+  double* Usave;           // optional row-major [R][MP]: u = H^T t
   // backward inputs / outputs
   const double* dmu;
   const double* dvar;
@@ -62,6 +62,7 @@ struct RowArgs {
   double* part_zf;         // [grid][MP]
   int want_param_grads;
   int want_x_grads;
+  int sm_reserve;          // backward product kernel: SMs to leave free for concurrent side-stream kernels
 };
 
 // Covariance parameters in the form the row kernels evaluate them: every exponential is 2^y with the -1/2 log2(e) / l^2
@@ -113,7 +114,7 @@ struct CovSmem {
   double dvar[ROWS], mask[ROWS];
   double zsT[kMaxD][MAX_MP];
   double zfs[MAX_MP];
-  double acc_zf[BWD ? NW : 1][MAX_MP];      // backward: per-warp d zf accumulators
+  double acc_zf[BWD ? NW : 1][BWD ? MAX_MP : 1];   // backward: per-warp d zf accumulators
   double acc_th[BWD ? NW : 1][MAX_THETA];   // backward: per-warp d theta accumulators (scalars | l1 | l2)
 };
 
@@ -126,34 +127,100 @@ __device__ __forceinline__ double* tile_ptr(unsigned char* smem) {
   return reinterpret_cast<double*>(smem + ((sizeof(RowSmem) + 127) / 128) * 128);
 }
 
+constexpr int FWD_NST = 4, BWD_NST = 4;   // A-fragment ring depth (k-steps) of the forward / backward product kernels
+__host__ __device__ inline size_t tile_bytes(int MP) { return (size_t)TR * (MP + 4) * sizeof(double); }
 __host__ inline size_t row_smem_bytes(int MP) {
-  return ((sizeof(RowSmem) + 127) / 128) * 128 + (size_t)TR * (MP + 4) * sizeof(double);
+  return ((sizeof(RowSmem) + 127) / 128) * 128 + tile_bytes(MP) + (size_t)ROW_WARPS * FWD_NST * 32 * sizeof(double2);
 }
 
 // One warp: acc(2 slabs x 16 rows x 32 cols) += A[slab rows, k-range] * B[k-range, 32 cols].
-// A: row-major MP x MP in global (L2-resident), triangular: LOWER uses k < 16(s+1), UPPER uses k >= 16 s.
+// Af: the MP x MP operator in A-fragment order (common.cuh frag_offset; L2-resident), triangular: LOWER uses
+// k < 16(s+1), UPPER uses k >= 16 s.  One 16-byte load per lane and k-step feeds both 8-row halves of the slab and a
+// warp's load is 512 contiguous bytes (4 L1 wavefronts; the row-major form cost 16 for the same data).
 // Bs: shared, Bs[col][k] with leading dimension ldb (ldb % 16 == 4 -> conflict-free fragment loads).
-template <bool UPPER>
-__device__ __forceinline__ void slab_gemm(double (&acc)[2][2][4][2], const double* __restrict__ A, int MP,
-                                          const double* Bs, int ldb, int sA, int sB, int half, int lane) {
+// 16-byte asynchronous global -> shared copy (L2 only) and its group bookkeeping.  The "memory" clobbers keep the
+// compiler from moving shared-memory reads across the wait.
+__device__ __forceinline__ void cp_async16_cg(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One warp: acc(2 slabs x 16 rows x 32 cols) += A[slab rows, k-range] * B[k-range, 32 cols].
+// Af: the MP x MP operator in A-fragment order (common.cuh frag_offset; L2-resident), triangular: LOWER uses
+// k < 16(s+1), UPPER uses k >= 16 s.  The fragments come from L2 (several hundred cycles, the top stall of the
+// register-loaded version: ncu long_scoreboard, profiles/r01r_*): each lane streams ITS 16-byte fragment of every
+// k-step through a private slot ring in shared memory with cp.async, NST - 1 k-steps (8 DMMAs each) ahead of its
+// use.  A lane only ever reads the slots it wrote itself, so cp.async.wait_group is the only synchronisation.
+// ring: this warp's NST x 32 double2 slots.
+// Bs: shared, Bs[col][k] with leading dimension ldb (ldb % 16 == 4 -> conflict-free fragment loads).
+template <bool UPPER, int NST, bool KSPLIT = false>
+__device__ __forceinline__ void slab_gemm(double (&acc)[2][2][4][2], const double* __restrict__ Af, int MP,
+                                          const double* Bs, int ldb, int sA, int sB, int half, int lane,
+                                          double2* ring) {
+  static_assert(NST == 4 || NST == 8, "ring depth");
   const int g = lane >> 2, t = lane & 3;
+  double2* slot = ring + lane;
+  const double* b0 = Bs + (size_t)(32 * half + g) * ldb + t;
+  const size_t ct_stride = (size_t)8 * ldb;
 #pragma unroll
   for (int sl = 0; sl < 2; ++sl) {
     const int s = sl == 0 ? sA : sB;
     const int kbeg = UPPER ? 16 * s : 0;
-    const int kend = UPPER ? MP : 16 * (s + 1);
-    const double* a0p = A + (size_t)(16 * s + g) * MP + t;
-    const double* a1p = a0p + (size_t)8 * MP;
-    const double* bp = Bs + (size_t)(32 * half + g) * ldb + t;
-#pragma unroll 4
-    for (int k0 = kbeg; k0 < kend; k0 += 4) {
-      const double a0 = __ldg(a0p + k0), a1 = __ldg(a1p + k0);
+    const int nq = (UPPER ? MP - 16 * s : 16 * (s + 1)) >> 2;      // k-steps of 4; a multiple of 4
+    // reads up to NST - 1 fragments past the slab's k-range: still inside the operator buffer (the fragment blocks are
+    // followed by at least 6 MP + 144 doubles, common.cuh), never used
+    const double2* ap = reinterpret_cast<const double2*>(Af) + ((size_t)s * (MP >> 2) + (kbeg >> 2)) * 32 + lane;
+    const double* bp = b0 + kbeg;
+    // KSPLIT: odd k-steps accumulate into a second register set, so consecutive k-steps of a warp are independent
+    // (DMMA latency ~140 cycles = 9 DMMA issue slots; needed when only two warps share a scheduler)
+    double acc2[KSPLIT ? 2 : 1][KSPLIT ? 4 : 1][2];
+    if (KSPLIT) {
 #pragma unroll
-      for (int ct = 0; ct < 4; ++ct) {
-        const double b = bp[(size_t)(8 * ct) * ldb + k0];
-        dmma884(acc[sl][0][ct][0], acc[sl][0][ct][1], a0, b);
-        dmma884(acc[sl][1][ct][0], acc[sl][1][ct][1], a1, b);
+      for (int ib = 0; ib < 2; ++ib)
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) { acc2[KSPLIT ? ib : 0][KSPLIT ? ct : 0][0] = 0.0; acc2[KSPLIT ? ib : 0][KSPLIT ? ct : 0][1] = 0.0; }
+    }
+#pragma unroll
+    for (int j = 0; j < NST - 1; ++j) {
+      cp_async16_cg(slot + j * 32, ap + j * 32);
+      cp_async_commit_group();
+    }
+    ap += (NST - 1) * 32;
+    for (int q0 = 0; q0 < nq; q0 += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // slot of k-step q + NST - 1 == slot of k-step q - 1, whose fragment this lane's DMMAs have already consumed
+        cp_async16_cg(slot + ((j + NST - 1) & (NST - 1)) * 32, ap + j * 32);
+        cp_async_commit_group();
+        cp_async_wait_group<NST - 1>();
+        const double2 av = slot[(j & (NST - 1)) * 32];
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) {
+          const double b = bp[ct * ct_stride + 4 * j];
+          if (KSPLIT && (j & 1)) {
+            dmma884(acc2[0][KSPLIT ? ct : 0][0], acc2[0][KSPLIT ? ct : 0][1], av.x, b);
+            dmma884(acc2[KSPLIT ? 1 : 0][KSPLIT ? ct : 0][0], acc2[KSPLIT ? 1 : 0][KSPLIT ? ct : 0][1], av.y, b);
+          } else {
+            dmma884(acc[sl][0][ct][0], acc[sl][0][ct][1], av.x, b);
+            dmma884(acc[sl][1][ct][0], acc[sl][1][ct][1], av.y, b);
+          }
+        }
       }
+      ap += 4 * 32;
+      bp += 16;
+    }
+    cp_async_wait_group<0>();   // the look-ahead copies: drain before the next slab reuses the slots
+    if (KSPLIT) {
+#pragma unroll
+      for (int ib = 0; ib < 2; ++ib)
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) {
+          acc[sl][ib][ct][0] += acc2[KSPLIT ? ib : 0][KSPLIT ? ct : 0][0];
+          acc[sl][ib][ct][1] += acc2[KSPLIT ? ib : 0][KSPLIT ? ct : 0][1];
+        }
     }
   }
 }
@@ -184,30 +251,26 @@ __device__ __forceinline__ void store_acc_to_tile(const double (&acc)[2][2][4][2
   }
 }
 
-__device__ __forceinline__ void save_acc_frag(const double (&acc)[2][2][4][2], double* dst, long long tile,
-                                              int nact, int wact, int lane) {
-  double* p = dst + (((size_t)tile * nact + wact) * 32) * 32 + lane;
+// accumulator fragments -> row-major [R][MP] rows in global memory (row r of the tile, operator index i): per store
+// instruction a warp writes 4 rows x 64 contiguous bytes (full 32-byte sectors); stores are fire-and-forget
+__device__ __forceinline__ void store_acc_rows(const double (&acc)[2][2][4][2], double* __restrict__ dst, long long row0,
+                                               int nvalid, int MP, int sA, int sB, int half, int lane) {
+  const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int sl = 0; sl < 2; ++sl)
+  for (int sl = 0; sl < 2; ++sl) {
+    const int s = sl == 0 ? sA : sB;
 #pragma unroll
-    for (int ib = 0; ib < 2; ++ib)
+    for (int ct = 0; ct < 4; ++ct)
 #pragma unroll
-      for (int ct = 0; ct < 4; ++ct)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) p[(size_t)(((sl * 2 + ib) * 4 + ct) * 2 + e) * 32] = acc[sl][ib][ct][e];
-}
-
-__device__ __forceinline__ void load_acc_frag(double (&acc)[2][2][4][2], const double* src, long long tile,
-                                              int nact, int wact, int lane) {
-  const double* p = src + (((size_t)tile * nact + wact) * 32) * 32 + lane;
-#pragma unroll
-  for (int sl = 0; sl < 2; ++sl)
-#pragma unroll
-    for (int ib = 0; ib < 2; ++ib)
-#pragma unroll
-      for (int ct = 0; ct < 4; ++ct)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) acc[sl][ib][ct][e] = p[(size_t)(((sl * 2 + ib) * 4 + ct) * 2 + e) * 32];
+      for (int e = 0; e < 2; ++e) {
+        const int r = 32 * half + 8 * ct + 2 * t + e;
+        if (r < nvalid) {
+          double* p = dst + (size_t)(row0 + r) * MP + 16 * s + g;
+          p[0] = acc[sl][0][ct][e];
+          p[8] = acc[sl][1][ct][e];
+        }
+      }
+  }
 }
 
 // loads the rows of one tile: x, propagated input f (sample of the previous layer's q(f), the fused
@@ -354,14 +417,15 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
   double* Ks = tile_ptr(smem_raw);
   const int MP = a.MP, ldb = MP + 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double2* ring = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(Ks) + tile_bytes(MP)) + warp * FWD_NST * 32;
   const int half = warp % NHALF, p = warp / NHALF;
   const int npairs = MP / 32, ns = MP / 16;
   const bool active = p < npairs;
   const int sA = p, sB = ns - 1 - p;
   const int nact = NHALF * npairs, wact = p * NHALF + half;
   const int g = lane >> 2, t = lane & 3;
-  const double* W = a.ops + ops_block(MP, OPS_W);
-  const double* G = a.ops + ops_block(MP, OPS_HT);
+  const double* W = a.ops + ops_block(MP, OPS_WF);
+  const double* G = a.ops + ops_block(MP, OPS_HTF);
   const double* beta = a.ops + ops_beta(MP);
 
   load_inducing(a, sm);
@@ -382,7 +446,7 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
     double acc[2][2][4][2];
     zero_acc(acc);
     if (active) {
-      slab_gemm<false>(acc, W, MP, Ks, ldb, sA, sB, half, lane);
+      slab_gemm<false, FWD_NST>(acc, W, MP, Ks, ldb, sA, sB, half, lane, ring);
       double pq[4][2], pm[4][2];
 #pragma unroll
       for (int ct = 0; ct < 4; ++ct)
@@ -428,7 +492,7 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
     // ---- u = H^T t ----
     if (active) {
       zero_acc(acc);
-      slab_gemm<true>(acc, G, MP, Ks, ldb, sA, sB, half, lane);
+      slab_gemm<true, FWD_NST>(acc, G, MP, Ks, ldb, sA, sB, half, lane, ring);
 #pragma unroll
       for (int ct = 0; ct < 4; ++ct)
 #pragma unroll
@@ -442,7 +506,7 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
           for (int o = 4; o < 32; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
           if (g == 0) sm.red[2][p][32 * half + 8 * ct + 2 * t + e] = q;
         }
-      if (a.Usave) save_acc_frag(acc, a.Usave, tile, nact, wact, lane);
+      if (a.Usave) store_acc_rows(acc, a.Usave, row0, nvalid, MP, sA, sB, half, lane);
     }
     __syncthreads();
     if (tid < nvalid) {
@@ -670,55 +734,113 @@ __device__ __forceinline__ void kgrad_tile_d(const RowArgs& a, SM& sm, const dou
 // ---------------------------------------------------------------------------------------------------
 struct BwdSmem {
   double dmu[TR], dvar[TR], mask[TR];
+  unsigned long long bar;     // mbarrier: the staged u / t rows of the next tile have landed
 };
-__host__ __device__ inline size_t bwd_smem_bytes(int MP) { return 1024 + (size_t)TR * (MP + 4) * sizeof(double); }
+// [BwdSmem | X tile | U stage | T stage | A-fragment rings]; tiles are [TR][MP + 4]
+__host__ __device__ inline size_t bwd_smem_bytes(int MP) {
+  return 1024 + 3 * tile_bytes(MP) + (size_t)ROW_WARPS * BWD_NST * 32 * sizeof(double2);
+}
 
-__global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_bwd_gemm_kernel(const __grid_constant__ RowArgs a) {
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+// bulk (TMA engine) global -> shared copy of `bytes` (multiple of 16, both sides 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes),
+               "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// One persistent CTA per SM.  The saved u and t rows of tile i+1 are staged into shared memory by the bulk-copy engine
+// while tile i's second product runs, and dk leaves straight from the accumulators, so no warp ever waits on HBM
+// (with the synchronous loads of the first version the memory phases cost 13 us of every 32 us tile and two CTAs per
+// SM did not hide them: profiles/r01z_*).  Per tile: y = H u (B operand read in place from the u stage), dt from y and
+// the t stage into the X tile, barrier, prefetch of the next tile, dk = W^T dt.
+__global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_gemm_kernel(const __grid_constant__ RowArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
-  double* Ks = reinterpret_cast<double*>(smem_raw + 1024);
   static_assert(sizeof(BwdSmem) <= 1024, "BwdSmem");
   const int MP = a.MP, ldb = MP + 4;
+  double* X = reinterpret_cast<double*>(smem_raw + 1024);
+  double* BU = reinterpret_cast<double*>(smem_raw + 1024 + tile_bytes(MP));
+  double* BT = reinterpret_cast<double*>(smem_raw + 1024 + 2 * tile_bytes(MP));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double2* ring = reinterpret_cast<double2*>(smem_raw + 1024 + 3 * tile_bytes(MP)) + warp * BWD_NST * 32;
   const int half = warp % NHALF, p = warp / NHALF;
   const int npairs = MP / 32, ns = MP / 16;
   const bool active = p < npairs;
   const int sA = p, sB = ns - 1 - p;
-  const int nact = NHALF * npairs, wact = p * NHALF + half;
   const int g = lane >> 2, t = lane & 3;
-  const double* WT = a.ops + ops_block(MP, OPS_WT);
-  const double* H = a.ops + ops_block(MP, OPS_H);
+  const double* WT = a.ops + ops_block(MP, OPS_WTF);
+  const double* H = a.ops + ops_block(MP, OPS_HF);
   const double* beta = a.ops + ops_beta(MP);
-
   const long long ntiles = (a.R + TR - 1) / TR;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const unsigned row_bytes = (unsigned)MP * sizeof(double);
+
+  if (tid == 0) {
+    mbar_init(&sm.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // warp 0: one bulk copy per row and array; invalid rows of a ragged last tile keep stale (finite or not, never
+  // stored: every column of the products depends on its own row only) data
+  auto stage_tile = [&](long long tile) {
     const long long row0 = tile * TR;
     const int nvalid = (int)min((long long)TR, a.R - row0);
-    if (tid < TR) {
-      const bool ok = tid < nvalid;
-      sm.dmu[tid] = ok ? a.dmu[row0 + tid] : 0.0;
-      sm.dvar[tid] = ok ? a.dvar[row0 + tid] : 0.0;
-      sm.mask[tid] = (ok && a.training && a.craw) ? (a.craw[row0 + tid] >= 0.0 ? 1.0 : 0.0) : 1.0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the stages -> async writes
+    if (lane == 0) mbar_expect_tx(&sm.bar, 2u * (unsigned)nvalid * row_bytes);
+    __syncwarp();
+    if (lane < nvalid) {
+      bulk_g2s(BU + (size_t)lane * ldb, a.Usave + (size_t)(row0 + lane) * MP, row_bytes, &sm.bar);
+      bulk_g2s(BT + (size_t)lane * ldb, a.Tsave + (size_t)(row0 + lane) * MP, row_bytes, &sm.bar);
     }
+  };
+  // per-row scalars of a tile, prefetched into registers of the first TR threads one tile ahead
+  double pf_dmu = 0.0, pf_dvar = 0.0, pf_mask = 1.0;
+  auto prefetch_rows = [&](long long tile) {
+    const long long row = tile * TR + tid;
+    const bool ok = row < a.R;
+    pf_dmu = ok ? a.dmu[row] : 0.0;
+    pf_dvar = ok ? a.dvar[row] : 0.0;
+    pf_mask = (ok && a.training && a.craw) ? (a.craw[row] >= 0.0 ? 1.0 : 0.0) : 1.0;
+  };
+
+  long long tile = blockIdx.x;
+  if (tile < ntiles) {
+    if (warp == 0) stage_tile(tile);
+    if (tid < TR) prefetch_rows(tile);
+  }
+  unsigned parity = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * TR;
+    const int nvalid = (int)min((long long)TR, a.R - row0);
+    if (tid < TR) { sm.dmu[tid] = pf_dmu; sm.dvar[tid] = pf_dvar; sm.mask[tid] = pf_mask; }
+    mbar_wait(&sm.bar, parity);
+    parity ^= 1u;
+    __syncthreads();
     double acc[2][2][4][2];
-    // ---- u tile -> shared (B layout) ----
     if (active) {
-      load_acc_frag(acc, a.Usave, tile, nact, wact, lane);
-      store_acc_to_tile(acc, Ks, ldb, sA, sB, half, lane);
-    }
-    __syncthreads();
-    // ---- y = H u ----
-    if (active) {
+      // ---- y = H u ----
       zero_acc(acc);
-      slab_gemm<false>(acc, H, MP, Ks, ldb, sA, sB, half, lane);
-    }
-    __syncthreads();   // u is no longer needed: stage the saved t tile through shared memory
-    for (int r = warp; r < TR; r += ROW_WARPS)
-      for (int j = lane; j < MP; j += 32)
-        Ks[(size_t)r * ldb + j] = r < nvalid ? a.Tsave[(size_t)(row0 + r) * MP + j] : 0.0;
-    __syncthreads();
-    // ---- dt = dmu beta - 2 dvar (mask t - y) ----
-    if (active) {
+      slab_gemm<false, BWD_NST, true>(acc, H, MP, BU, ldb, sA, sB, half, lane, ring);
+      // ---- dt = dmu beta - 2 dvar (mask t - y) ----
 #pragma unroll
       for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
@@ -730,25 +852,24 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_bwd_gemm_ker
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int r = 32 * half + 8 * ct + 2 * t + e;
-              const double tv = Ks[(size_t)r * ldb + i];
+              const double tv = BT[(size_t)r * ldb + i];
               acc[sl][ib][ct][e] = sm.dmu[r] * bi - 2.0 * sm.dvar[r] * (sm.mask[r] * tv - acc[sl][ib][ct][e]);
             }
         }
+      store_acc_to_tile(acc, X, ldb, sA, sB, half, lane);
     }
-    __syncthreads();
-    if (active) store_acc_to_tile(acc, Ks, ldb, sA, sB, half, lane);
-    __syncthreads();
-    // ---- dk = W^T dt ----
+    __syncthreads();   // dt complete in X; the u / t stages and the row scalars are free
+    const long long next = tile + gridDim.x;
+    if (next < ntiles) {
+      if (warp == 0) stage_tile(next);
+      if (tid < TR) prefetch_rows(next);
+    }
+    // ---- dk = W^T dt, straight from the accumulators to HBM ----
     if (active) {
       zero_acc(acc);
-      slab_gemm<true>(acc, WT, MP, Ks, ldb, sA, sB, half, lane);
+      slab_gemm<true, BWD_NST, true>(acc, WT, MP, X, ldb, sA, sB, half, lane, ring);
+      store_acc_rows(acc, a.dk, row0, nvalid, MP, sA, sB, half, lane);
     }
-    __syncthreads();
-    if (active) store_acc_to_tile(acc, Ks, ldb, sA, sB, half, lane);
-    __syncthreads();
-    for (int r = warp; r < nvalid; r += ROW_WARPS)
-      for (int j = lane; j < MP; j += 32) a.dk[(size_t)(row0 + r) * MP + j] = Ks[(size_t)r * ldb + j];
-    __syncthreads();
   }
 }
 
@@ -1020,6 +1141,18 @@ int kgrad_grid(long long R) {
 
 // product kernel (dk into a.dk) followed by the covariance-gradient kernel; per-CTA partials of the latter are
 // indexed by ITS grid (kgrad_grid)
+// grid of the backward product kernel: one persistent CTA per SM, minus `reserve` SMs; then the smallest grid that
+// needs the same number of tile rounds (the freed SMs run the concurrent side-stream kernels of the fused step: with
+// every SM's registers and shared memory taken by this kernel they would otherwise wait for it to finish)
+int row_bwd_grid(long long R, int reserve) {
+  const long long ntiles = (R + TR - 1) / TR;
+  long long cap = num_sms() - reserve;
+  if (cap < 1) cap = 1;
+  if (ntiles <= cap) return (int)(ntiles > 0 ? ntiles : 1);
+  const long long rounds = (ntiles + cap - 1) / cap;
+  return (int)((ntiles + rounds - 1) / rounds);
+}
+
 int launch_row_bwd(const RowArgs& a, cudaStream_t st) {
   if (a.MP % 32 != 0 || a.MP > MAX_MP || a.d > kMaxD || a.M > a.MP) return -2;
   static bool attr_done = false;
@@ -1031,8 +1164,10 @@ int launch_row_bwd(const RowArgs& a, cudaStream_t st) {
     attr_done = true;
   }
   if (a.R <= 0) return 0;
+  if (((uintptr_t)a.Tsave | (uintptr_t)a.Usave) & 15) return -2;   // bulk copies need 16-byte aligned rows
+  const int grid_b = row_bwd_grid(a.R, a.sm_reserve);
   MOBO_LAUNCH("row_bwd_gemm_kernel", st,
-              row_bwd_gemm_kernel<<<row_grid(a.R), ROW_THREADS, bwd_smem_bytes(a.MP), st>>>(a));
+              row_bwd_gemm_kernel<<<grid_b, ROW_THREADS, bwd_smem_bytes(a.MP), st>>>(a));
   const int grid = kgrad_grid(a.R);
   const size_t smem = sizeof(KgSmem);
   if (a.want_param_grads && a.want_x_grads) {

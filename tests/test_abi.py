@@ -38,6 +38,6 @@ def test_ctypes_signatures_match_header():
 def test_size_queries():
     lib = _lib.load()
     assert lib.mobo_padded_m(16) == 32 and lib.mobo_padded_m(256) == 256 and lib.mobo_padded_m(75) == 96
-    assert lib.mobo_ops_doubles(256) == 7 * 256 * 256 + 6 * 256 + 16 + 128
+    assert lib.mobo_ops_doubles(256) == 11 * 256 * 256 + 6 * 256 + 16 + 128
     assert lib.mobo_rows_save_doubles(256, 65536) == 65536 * 256
     assert lib.mobo_rows_save_doubles(16, 10) == 32 * 32
