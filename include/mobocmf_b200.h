@@ -172,6 +172,20 @@ int mobo_acq_moments(int fidelity, int d, int M, int S, long long n, const doubl
 /* out[i] (+)= 1/2 max(0, log vu[i] - log vc[i])   (_JES_MFDGP.forward, acquisition_functions/JESMOC_MFDGP.py:52) */
 int mobo_jes(const double* var_uncond, const double* var_cond, long long n, int accumulate, double* out, void* stream);
 
+/* ---- Pareto-sample generation ----
+ * Values (and optionally the x-gradient of the top layer) of the random-Fourier-feature function samples of an MFDGP
+ * layer chain at n points: the closures returned by MFDGPHiddenLayer._sample_from_posterior(_layer0) /
+ * _sample_from_prior(_layer0) (mobocmf/layers/mfdgp_hidden_layer.py:311-514) as MOOP evaluates them on its grid
+ * (mobocmf/util/moop.py:221-286).  params[l] (device): layer 0 [W (F x d) | b (F) | theta (F)], layer >= 1
+ * [W_x1 (F x d) | W_f (F) | W_x2 (F x d) | b_x1 (F) | b_x2 (F) | theta (3 F)].  scales (HOST, L x 3): layer 0
+ * {sqrt(2 alpha / F), -, -}, layer >= 1 {sqrt(2 alpha_x1 / F) sqrt(nu_lin), sqrt(2 alpha_x1 alpha_f / F),
+ * sqrt(2 alpha_x2 / F)}.  f: L x n (every layer's sample); grad: n x d or NULL.  L <= 4, d <= 8. */
+int mobo_rff_eval(int L, int d, int F, const double* const* params, const double* scales, const double* x, long long n,
+                  double* f, double* grad, void* stream);
+/* mask[j] = 1 iff point j of pts (n x k, k <= 8, minimisation) is not dominated (MOOP.compute_pareto_front,
+ * mobocmf/util/moop.py:141-185); of exact duplicates the lowest index survives. */
+int mobo_pareto_mask(const double* pts, long long n, int k, unsigned char* mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

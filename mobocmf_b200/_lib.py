@@ -47,6 +47,9 @@ _SIGNATURES = {
     "mobo_acq_moments": (_c_i, [_c_i, _c_i, _c_i, _c_i, _c_ll, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_d, _c_d,
                                 _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
     "mobo_jes": (_c_i, [_c_dp, _c_dp, _c_ll, _c_i, _c_dp, _c_dp]),
+    # Pareto-sample generation
+    "mobo_rff_eval": (_c_i, [_c_i, _c_i, _c_i, _c_dp, _c_dp, _c_dp, _c_ll, _c_dp, _c_dp, _c_dp]),
+    "mobo_pareto_mask": (_c_i, [_c_dp, _c_ll, _c_i, _c_dp, _c_dp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -6,6 +6,7 @@
 #include "opchain.cu"
 #include "row_pass.cu"
 #include "step.cu"
+#include "rff.cu"
 
 using namespace mobo;
 
@@ -601,6 +602,23 @@ int mobo_jes(const double* var_uncond, const double* var_cond, long long n, int 
   MOBO_LAUNCH("jes_kernel", st,
               jes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(var_uncond, var_cond, out, n, accumulate));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int mobo_rff_eval(int L, int d, int F, const double* const* params, const double* scales, const double* x, long long n,
+                  double* f, double* grad, void* stream) {
+  if (L < 1 || L > RFF_MAX_LAYERS) return -2;
+  RffArgs a;
+  a.L = L; a.d = d; a.F = F; a.want_grad = grad != nullptr;
+  for (int l = 0; l < RFF_MAX_LAYERS; ++l) {
+    a.params[l] = l < L ? params[l] : nullptr;
+    for (int q = 0; q < 3; ++q) a.scale[l][q] = l < L ? scales[3 * l + q] : 0.0;
+  }
+  a.x = x; a.n = n; a.f = f; a.grad = grad;
+  return launch_rff_eval(a, (cudaStream_t)stream);
+}
+
+int mobo_pareto_mask(const double* pts, long long n, int k, unsigned char* mask, void* stream) {
+  return launch_pareto_mask(pts, n, k, mask, (cudaStream_t)stream);
 }
 
 }  // extern "C"

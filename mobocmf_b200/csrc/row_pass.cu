@@ -422,7 +422,6 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
   const int npairs = MP / 32, ns = MP / 16;
   const bool active = p < npairs;
   const int sA = p, sB = ns - 1 - p;
-  const int nact = NHALF * npairs, wact = p * NHALF + half;
   const int g = lane >> 2, t = lane & 3;
   const double* W = a.ops + ops_block(MP, OPS_WF);
   const double* G = a.ops + ops_block(MP, OPS_HTF);

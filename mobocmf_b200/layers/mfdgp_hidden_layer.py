@@ -8,7 +8,8 @@ Differences from the reference that are deliberate:
   generator stream (SURVEY.md quirk Q6); by default they are drawn on the device;
 * the eval branch computes only the diagonal of the predictive covariance (the reference materialises R x R and
   reads its diagonal).
-The RFF function sampling (``sample_from_posterior`` / ``sample_from_prior``) is outside the hot path.
+``sample_from_posterior`` / ``sample_from_prior`` (RFF function samples, :288-514) return ``mobocmf_b200.rff.RFFSample``
+objects evaluated by ``mobo_rff_eval``.
 """
 from typing import Optional
 
@@ -213,6 +214,15 @@ class MFDGPHiddenLayer(nn.Module):
 
     def eval_mode(self):
         self._eval_mode = True
+
+    # ---- random-Fourier-feature function samples (layers/mfdgp_hidden_layer.py:311-514) ----
+    def sample_from_posterior(self, input_dim, sample_from_posterior_last_layer=None, nFeatures=500):
+        from .. import rff
+        return rff.sample_layer(self, input_dim, sample_from_posterior_last_layer, nFeatures, prior=False)
+
+    def sample_from_prior(self, input_dim, sample_from_prior_last_layer=None, nFeatures=500):
+        from .. import rff
+        return rff.sample_layer(self, input_dim, sample_from_prior_last_layer, nFeatures, prior=True)
 
     # ---- kernel-facing views of the parameters ----
     @property

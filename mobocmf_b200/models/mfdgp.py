@@ -248,6 +248,23 @@ class MFDGP(nn.Module):
     # ---- fused acquisition chain (mobo_acq_moments): no autograd graph, one enqueue per model ----
     ACQ_CHUNK = 1 << 18      # candidates per enqueue (bounds the n * S scratch)
 
+    # ---- function samples of every layer (models/mfdgp.py:264-288) ----
+    def sample_function_from_each_layer(self, nFeatures=500):
+        result, last = [], None
+        for i in range(self.num_hidden_layers):
+            last = getattr(self, self.name_hidden_layer + str(i)).sample_from_posterior(self.input_dims, last,
+                                                                                        nFeatures=nFeatures)
+            result.append(last)
+        return result
+
+    def sample_function_from_prior_each_layer(self, nFeatures=500):
+        result, last = [], None
+        for i in range(self.num_hidden_layers):
+            last = getattr(self, self.name_hidden_layer + str(i)).sample_from_prior(self.input_dims, last,
+                                                                                    nFeatures=nFeatures)
+            result.append(last)
+        return result
+
     def _fused_acquisition_applies(self, x):
         if self.training or self.use_only_highest_fidelity is True or not x.is_cuda or x.dtype != torch.float64:
             return False

@@ -3,8 +3,9 @@
 (``_update_conditioned_models``, :272-346) and the theta / omega factors (:227-243).  Orchestration stays Python;
 every MFDGP forward / backward inside the steps runs on the sm_100a kernels.
 
-Out of the hot path and therefore not provided here: RFF posterior function sampling + MOOP Pareto-set extraction
-(``sample_and_store_pareto_solution``, :181-225).  Set ``pareto_set`` / ``pareto_front`` on the fitter instead.
+``sample_and_store_pareto_solution`` (:181-225) draws one RFF function sample per black box
+(``MFDGP.sample_function_from_each_layer``) and extracts the Pareto set with ``mobocmf_b200.util.moop.MOOP``; the grid
+evaluation and the non-dominated cull run on the GPU.
 """
 import sys
 import warnings
@@ -17,6 +18,7 @@ from ..fused import Adam
 from ..gp import settings
 from ..mlls.variational_elbo_mf import VariationalELBOMF
 from ..models.mfdgp import MFDGP, TL
+from .moop import MOOP, NotFeasiblePoints
 
 ITER_PRINT = 1000
 
@@ -194,9 +196,36 @@ class BlackBoxMFDGPFitter():
                           lr=self.lr_2)
         self.models_uncond_trained = True
 
+    def _sample_and_store_pareto_solution(self):
+        """fitter.py:181-217: one function sample of the top layer per objective; constraints are re-drawn until the
+        grid has a feasible point (MAX_TRIES_FOR_FEASIBLE_GRID), then the least infeasible point is accepted."""
+        l_samples_objs = [h.mfdgp.sample_function_from_each_layer()[-1] for h in self.mfdgp_handlers_objs.values()]
+        inputs = self.x_train
+        global_optimizer = None
+        for _ in range(MFDGPHandler.MAX_TRIES_FOR_FEASIBLE_GRID):
+            l_samples_cons = [h.mfdgp.sample_function_from_each_layer()[-1] for h in self.mfdgp_handlers_cons.values()]
+            global_optimizer = MOOP(l_samples_objs, l_samples_cons, input_dim=inputs.shape[1],
+                                    grid_size=self.opt_grid_size * inputs.shape[1],
+                                    pareto_set_size=self.pareto_set_size,
+                                    feasible_values=-1.0 * self.thresholds_cons.cpu().numpy())
+            res = global_optimizer.compute_pareto_solution_from_samples(inputs)
+            if res is not None:
+                self.pareto_set, self.pareto_front, self.samples_objs, self.samples_cons = res
+                return res
+        res = global_optimizer.compute_pareto_solution_from_samples(inputs, allow_negative_constraints=True)
+        if res is not None:
+            self.pareto_set, self.pareto_front, self.samples_objs, self.samples_cons = res
+            return res
+        raise NotFeasiblePoints("[ERROR] No feasible points were found in the constraint space! # tries: %d."
+                                % MFDGPHandler.MAX_TRIES_FOR_FEASIBLE_GRID)
+
     def sample_and_store_pareto_solution(self):
-        raise NotImplementedError("Pareto-set sampling (RFF + MOOP) is outside the B200 hot path (SURVEY.md §8); "
-                                  "set fitter.pareto_set / fitter.pareto_front")
+        while True:
+            try:
+                return self._sample_and_store_pareto_solution()
+            except NotFeasiblePoints:
+                print("Not feasible solution found, trying another time!")
+                sys.stdout.flush()
 
     # ---- theta / omega factors (fitter.py:227-243) ----
     def loss_theta_factors(self, cs_mean, cs_var, threshold):
