@@ -319,6 +319,8 @@ def run_ours(args):
         if acq:
             out["acq"] = acq
         if not args.no_acq and world == 1:
+            out["pareto_sampling"] = bench_pareto(dev, with_cpu=not args.no_cpu)
+        if not args.no_acq and world == 1:
             out["small_configs"] = bench_small_configs(dev)
         if not args.no_cpu and world == 1:      # reported on rank 0 at N = 1 only
             out["cpu_baseline"] = cpu_baseline(cfg, x, y, fid, model, max_seconds=25.0, steps=10, warmup=2)
@@ -474,6 +476,62 @@ def bench_acq(model, dev, cfg, world, n=8192, K=6, P=16, iters=2):
             "candidates_per_gpu": n, "n_gpus": world, "ms_per_sweep": ms, "model_chains_per_candidate": chains,
             "model_chain_evals_per_s": world * n * chains / (ms * 1e-3), "rows_per_s": world * rows / (ms * 1e-3),
             "tflops_per_gpu": flop / (ms * 1e-3) / 1e12, "acq_mean": float(out.mean())}
+
+
+def bench_pareto(dev, d=6, L=3, F=500, K=6, iters=5, with_cpu=True):
+    """Pareto-sample generation at the C5 shape: K = 6 black boxes, each one RFF function
+    sample of a 3-layer chain (F = 500 features per kernel), evaluated on MOOP's grid of 1000 d^2 = 36 000 points
+    (mobocmf/util/moop.py:231), then the non-dominated cull of the 4 objectives.  Random draws as in
+    _sample_from_prior (no model needed: the evaluation cost does not depend on theta)."""
+    import numpy as np
+    from mobocmf_b200.rff import RFFSample
+    from mobocmf_b200.util.moop import pareto_mask
+    rng = np.random.RandomState(0)
+    n = 1000 * d * d
+
+    def chain():
+        t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+        c = [dict(kind=0, nF=F, W=t(rng.normal(size=(F, d)) / (0.25 * d)), b=t(rng.uniform(0, 2 * np.pi, size=(F, 1))),
+                  theta=t(rng.normal(size=F)), alpha=1.0)]
+        for _ in range(L - 1):
+            c.append(dict(kind=1, nF=F, W_x1=t(rng.normal(size=(F, d)) / (2.5 * d)), W_f=t(rng.normal(size=F)),
+                          W_x2=t(rng.normal(size=(F, d)) / (0.25 * d)), b_x1=t(rng.uniform(0, 2 * np.pi, size=(F, 1))),
+                          b_x2=t(rng.uniform(0, 2 * np.pi, size=(F, 1))), theta=t(rng.normal(size=3 * F)), alpha_x1=1.0,
+                          alpha_x1f=1.0, alpha_x2=0.01, nu_lin=1.0))
+        return c
+    chains = [chain() for _ in range(K)]
+    samples = [RFFSample(c, d, F, dev) for c in chains]
+    grid = torch.as_tensor(rng.uniform(size=(n, d)), device=dev)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    vals = None
+    for it in range(iters + 2):
+        if it == 2:
+            e0.record()
+        vals = torch.stack([s(grid) for s in samples[:4]] + [s(grid) for s in samples[4:]], dim=1)
+    e1.record()
+    for it in range(iters):
+        mask = pareto_mask(vals[:, :4].contiguous())
+    e2.record()
+    torch.cuda.synchronize()
+    ms_eval, ms_cull = e0.elapsed_time(e1) / iters, e1.elapsed_time(e2) / iters
+    # FP64-pipe work per (point, sample): features x (dot products + cos); one fp64 cos ~ 45 DFMA-equivalents (estimate)
+    cos_cost = 45
+    per_point = F * (2 * d + cos_cost) + (L - 1) * F * (4 * d + 8 + 3 * cos_cost)
+    out = {"metric": "rff_grid_evals_per_s", "value": K * n / (ms_eval * 1e-3), "unit": "grid points x function samples / s",
+           "config": "C5 shape: d=6, 3-layer chains, F=500, %d-point grid, %d samples per pass" % (n, K),
+           "ms_per_pass": ms_eval, "fp64_tflops_estimate": K * n * per_point * 2 / (ms_eval * 1e-3) / 1e12,
+           "pareto_cull_ms": ms_cull, "pareto_points": int(mask.sum()), "cull_pairs_per_s": n * n / (ms_cull * 1e-3)}
+    if with_cpu:
+        from oracle import rff_moop_oracle as R
+        cpu_chain = [{k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in s.items()} for s in chains[0]]
+        xs = grid[:4096].cpu().numpy()
+        t0 = time.time()
+        ref = R.eval_chain(cpu_chain, xs)[-1]
+        t_cpu = time.time() - t0
+        out["cpu_baseline"] = {"value": 4096 / t_cpu, "unit": out["unit"], "cores": os.cpu_count(), "kind": "port",
+                               "sample": "numpy oracle, one sample on 4096 of the grid points (%.2f s)" % t_cpu,
+                               "max_abs_diff_vs_gpu": float(np.abs(ref - vals[:4096, 0].cpu().numpy()).max())}
+    return out
 
 
 def cpu_baseline(cfg, x, y, fid, model, max_seconds=30.0, steps=3, warmup=1):
