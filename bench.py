@@ -514,12 +514,12 @@ def bench_pareto(dev, d=6, L=3, F=500, K=6, iters=5, with_cpu=True):
     e2.record()
     torch.cuda.synchronize()
     ms_eval, ms_cull = e0.elapsed_time(e1) / iters, e1.elapsed_time(e2) / iters
-    # FP64-pipe work per (point, sample): features x (dot products + cos); one fp64 cos ~ 45 DFMA-equivalents (estimate)
-    cos_cost = 45
-    per_point = F * (2 * d + cos_cost) + (L - 1) * F * (4 * d + 8 + 3 * cos_cost)
+    cos_per_point = F + (L - 1) * 3 * F        # one fp64 cos per (point, feature): 3500 per point and sample here
     out = {"metric": "rff_grid_evals_per_s", "value": K * n / (ms_eval * 1e-3), "unit": "grid points x function samples / s",
            "config": "C5 shape: d=6, 3-layer chains, F=500, %d-point grid, %d samples per pass" % (n, K),
-           "ms_per_pass": ms_eval, "fp64_tflops_estimate": K * n * per_point * 2 / (ms_eval * 1e-3) / 1e12,
+           "ms_per_pass": ms_eval, "fp64_cos_per_s": K * n * cos_per_point / (ms_eval * 1e-3),
+           "roofline_note": "FP64-pipe bound (DFMA + cos polynomial): ncu sm__inst_executed_pipe_fp64 35% of peak, "
+                            "issue slots 60% (profiles/r01z_ncu_full_summary_rff_pareto.txt)",
            "pareto_cull_ms": ms_cull, "pareto_points": int(mask.sum()), "cull_pairs_per_s": n * n / (ms_cull * 1e-3)}
     if with_cpu:
         from oracle import rff_moop_oracle as R
