@@ -531,13 +531,35 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
 //   th[0] = sum gk a1 E1 gg  (d/da1 = th[0] / a1)     th[1] = sum gk a1 E1 f f'   (d/dv)
 //   th[2] = sum gk a1 E1 af Ef (d/daf = th[2] / af)   th[3] = sum gk a1 E1 af Ef (f-f')^2  (d/dlf = th[3] / lf^3)
 //   th[4] = sum gk a2 E2     (d/da2 = th[4] / a2)     tl1[c], tl2[c] = sum g D_c^2  (d/dl_c = tl / l_c^3)
+// dk reaches the warp through a private 3-chunk cp.async ring (kg_ring, [chunk % 3][row][lane]): a lane copies the
+// RPW values it will use two chunks ahead of their use (the synchronous loads were 21 % of the kernel's stall samples,
+// profiles/r01r_*); rows past the end and padded inducing points are zero-filled by the copy.
+constexpr int KG_NST = 3;
+__device__ __forceinline__ void kg_issue(const double* __restrict__ Ks, int ldb, int rbase, int nvalid, int M, int ch,
+                                         int nch, double* ring, int lane) {
+  if (ch < nch) {
+    const int j = 32 * ch + lane;
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const bool ok = j < M && rbase + i < nvalid;
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(ring + ((ch % KG_NST) * RPW + i) * 32 + lane);
+      const int sz = ok ? 8 : 0;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa),
+                   "l"(ok ? Ks + (size_t)(rbase + i) * ldb + j : Ks), "r"(sz) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 template <int KIND, int D, bool PARAM, bool XGRAD, bool SHX, class SM>
 __device__ __forceinline__ void kgrad_tile(const RowArgs& a, SM& sm, const double* __restrict__ Ks, int ldb,
-                                           long long row0, int nvalid, int warp, int lane) {
+                                           long long row0, int nvalid, int warp, int lane, double* ring) {
   const KernFast& kf = sm.kf;
   const double* tab = sm.e2tab;
   const int M = a.M, nch = a.MP / 32;
   const int rbase = warp * RPW;
+  kg_issue(Ks, ldb, rbase, nvalid, M, 0, nch, ring, lane);
+  kg_issue(Ks, ldb, rbase, nvalid, M, 1, nch, ring, lane);
   // register budget: the accumulators below stay in registers for the whole tile, so the per-dimension coefficients
   // and the rows' coordinates are re-read from shared memory (broadcast loads) instead of being cached
   const double la1 = kf.la1, la2 = kf.la2, laf = kf.laf, cf = kf.cf, vlin = kf.vlin, ilf = kf.ilf;
@@ -555,11 +577,13 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, SM& sm, const doubl
 
   for (int ch = 0; ch < nch; ++ch) {
     const int j = 32 * ch + lane;
+    kg_issue(Ks, ldb, rbase, nvalid, M, ch + 2, nch, ring, lane);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    const double* gring = ring + (ch % KG_NST) * RPW * 32 + lane;     // this lane's dk of the chunk: gring[32 i]
     double z[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) z[c] = sm.zsT[c][j];
     const double zf = sm.zfs[j], vz = vlin * zf;
-    const bool jok = j < M;
     double azf = 0.0;
     if (SHX && KIND == 1) {
       // the warp's rows share x: distances, a1 E1 and a2 E2 once per inducing point; the lengthscale (and x)
@@ -577,7 +601,7 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, SM& sm, const doubl
       double G1 = 0.0, G2 = 0.0;
 #pragma unroll
       for (int i = 0; i < RPW; ++i) {
-        const double gk = (jok && rbase + i < nvalid) ? Ks[(size_t)(rbase + i) * ldb + j] : 0.0;
+        const double gk = gring[32 * i];
         const double fi = sm.fs[rbase + i];
         const double dff = fi - zf, dff2 = dff * dff;
         const double Efp = exp2_tab(fma(dff2, cf, laf), tab);
@@ -607,7 +631,7 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, SM& sm, const doubl
     } else {
 #pragma unroll 2
     for (int i = 0; i < RPW; ++i) {
-      const double gk = (jok && rbase + i < nvalid) ? Ks[(size_t)(rbase + i) * ldb + j] : 0.0;
+      const double gk = gring[32 * i];
       const double fi = sm.fs[rbase + i];
       double diff[D], d2[D], D1 = la1, D2 = la2;
 #pragma unroll
@@ -658,6 +682,7 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, SM& sm, const doubl
     }
     if (PARAM && KIND == 1) sm.acc_zf[warp][j] += azf;   // one owner per slot -> deterministic
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   // row-wise sums over the inducing points, and the diag term d k_xx of the variance
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
@@ -707,16 +732,16 @@ __device__ __forceinline__ void kgrad_tile(const RowArgs& a, SM& sm, const doubl
 
 template <int KIND, bool PARAM, bool XGRAD, bool SHX, class SM>
 __device__ __forceinline__ void kgrad_tile_d(const RowArgs& a, SM& sm, const double* Ks, int ldb, long long row0,
-                                             int nvalid, int warp, int lane) {
+                                             int nvalid, int warp, int lane, double* ring) {
   switch (sm.kf.d) {
-    case 1: kgrad_tile<KIND, 1, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    case 2: kgrad_tile<KIND, 2, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    case 3: kgrad_tile<KIND, 3, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    case 4: kgrad_tile<KIND, 4, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    case 5: kgrad_tile<KIND, 5, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    case 6: kgrad_tile<KIND, 6, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    case 7: kgrad_tile<KIND, 7, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
-    default: kgrad_tile<KIND, 8, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane); break;
+    case 1: kgrad_tile<KIND, 1, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane, ring); break;
+    case 2: kgrad_tile<KIND, 2, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane, ring); break;
+    case 3: kgrad_tile<KIND, 3, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane, ring); break;
+    case 4: kgrad_tile<KIND, 4, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane, ring); break;
+    case 5: kgrad_tile<KIND, 5, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane, ring); break;
+    case 6: kgrad_tile<KIND, 6, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane, ring); break;
+    case 7: kgrad_tile<KIND, 7, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane, ring); break;
+    default: kgrad_tile<KIND, 8, PARAM, XGRAD, SHX>(a, sm, Ks, ldb, row0, nvalid, warp, lane, ring); break;
   }
 }
 
@@ -875,6 +900,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_gemm_kernel(const __gr
 // ---- through the covariance function: 4 warps x RPW rows per tile, 3 CTAs per SM ----
 constexpr int KG_WARPS = 4, KG_THREADS = KG_WARPS * 32, KG_ROWS = KG_WARPS * RPW, KG_CTAS_PER_SM = 3;
 using KgSmem = CovSmem<KG_WARPS, true>;
+__host__ __device__ inline size_t kg_smem_bytes() {
+  return ((sizeof(KgSmem) + 127) / 128) * 128 + (size_t)KG_WARPS * 3 * RPW * 32 * sizeof(double);
+}
 
 template <bool PARAM, bool XGRAD>
 __global__ void __launch_bounds__(KG_THREADS, KG_CTAS_PER_SM) kgrad_kernel(const __grid_constant__ RowArgs a) {
@@ -888,22 +916,44 @@ __global__ void __launch_bounds__(KG_THREADS, KG_CTAS_PER_SM) kgrad_kernel(const
   if (lane < MAX_THETA) sm.acc_th[warp][lane] = 0.0;
   __syncthreads();
 
-  const long long ntiles = (a.R + KG_ROWS - 1) / KG_ROWS;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long row0 = tile * KG_ROWS;
-    const int nvalid = (int)min((long long)KG_ROWS, a.R - row0);
-    load_tile_rows(a, sm, row0, nvalid);
-    if (tid < KG_ROWS) {
-      const bool ok = tid < nvalid;
-      sm.dvar[tid] = ok ? a.dvar[row0 + tid] : 0.0;
-      sm.mask[tid] = (ok && a.training && a.craw) ? (a.craw[row0 + tid] >= 0.0 ? 1.0 : 0.0) : 1.0;
+  // every warp walks its own groups of RPW rows: the rows' state lives in the warp's slice of the shared arrays and
+  // nothing is exchanged between warps until the final flush, so there is no CTA barrier in the loop (the per-tile
+  // barriers of the first version were 14 % of the stall samples)
+  double* ring = reinterpret_cast<double*>(smem_raw + ((sizeof(KgSmem) + 127) / 128) * 128) + warp * KG_NST * RPW * 32;
+  const int rbase = warp * RPW;
+  const long long ngroups = (a.R + RPW - 1) / RPW;
+  for (long long grp = (long long)blockIdx.x * KG_WARPS + warp; grp < ngroups; grp += (long long)gridDim.x * KG_WARPS) {
+    const long long rw0 = grp * RPW;                         // first row of the group (>= rbase)
+    const int nv = (int)min((long long)RPW, a.R - rw0);
+    __syncwarp();
+    for (int idx = lane; idx < RPW * d; idx += 32) {
+      const int r = idx / d, c = idx - r * d;
+      sm.xs[rbase + r][c] = r < nv ? a.x[(size_t)((rw0 + r) / a.xrep) * d + c] : 0.0;
     }
-    __syncthreads();
+    if (lane < RPW) {
+      const bool ok = lane < nv;
+      const long long row = rw0 + lane;
+      double f = 0.0;
+      if (ok && a.kind == 1) {
+        if (a.f_direct) {
+          f = a.f_direct[row];
+        } else {
+          const long long pr = row / a.prep;
+          f = a.mu_prev[pr] + sqrt(fmax(a.var_prev[pr], kMinVariance)) * a.eps[row % a.eps_mod];
+        }
+      }
+      sm.fs[rbase + lane] = f;
+      sm.dvar[rbase + lane] = ok ? a.dvar[row] : 0.0;
+      sm.mask[rbase + lane] = (ok && a.training && a.craw) ? (a.craw[row] >= 0.0 ? 1.0 : 0.0) : 1.0;
+    }
+    __syncwarp();
+    // kgrad_tile addresses rows as (tile row0) + rbase + i with validity rbase + i < nvalid
+    const long long row0 = rw0 - rbase;
+    const int nvalid = rbase + nv;
     const double* dk = a.dk + (size_t)row0 * MP;
-    if (a.kind == 0) kgrad_tile_d<0, PARAM, XGRAD, false>(a, sm, dk, MP, row0, nvalid, warp, lane);
-    else if (warp_rows_share_x(a, row0, warp)) kgrad_tile_d<1, PARAM, XGRAD, true>(a, sm, dk, MP, row0, nvalid, warp, lane);
-    else kgrad_tile_d<1, PARAM, XGRAD, false>(a, sm, dk, MP, row0, nvalid, warp, lane);
-    __syncthreads();
+    if (a.kind == 0) kgrad_tile_d<0, PARAM, XGRAD, false>(a, sm, dk, MP, row0, nvalid, warp, lane, ring);
+    else if (warp_rows_share_x(a, row0, warp)) kgrad_tile_d<1, PARAM, XGRAD, true>(a, sm, dk, MP, row0, nvalid, warp, lane, ring);
+    else kgrad_tile_d<1, PARAM, XGRAD, false>(a, sm, dk, MP, row0, nvalid, warp, lane, ring);
   }
   if (PARAM) {
     // ---- flush the per-CTA partials (fixed summation order -> deterministic) ----
@@ -1157,9 +1207,9 @@ int launch_row_bwd(const RowArgs& a, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(row_bwd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(MAX_MP));
-    cudaFuncSetAttribute(kgrad_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KgSmem));
-    cudaFuncSetAttribute(kgrad_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KgSmem));
-    cudaFuncSetAttribute(kgrad_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KgSmem));
+    cudaFuncSetAttribute(kgrad_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg_smem_bytes());
+    cudaFuncSetAttribute(kgrad_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg_smem_bytes());
+    cudaFuncSetAttribute(kgrad_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg_smem_bytes());
     attr_done = true;
   }
   if (a.R <= 0) return 0;
@@ -1168,7 +1218,7 @@ int launch_row_bwd(const RowArgs& a, cudaStream_t st) {
   MOBO_LAUNCH("row_bwd_gemm_kernel", st,
               row_bwd_gemm_kernel<<<grid_b, ROW_THREADS, bwd_smem_bytes(a.MP), st>>>(a));
   const int grid = kgrad_grid(a.R);
-  const size_t smem = sizeof(KgSmem);
+  const size_t smem = kg_smem_bytes();
   if (a.want_param_grads && a.want_x_grads) {
     MOBO_LAUNCH("kgrad_kernel<param,x>", st, kgrad_kernel<true, true><<<grid, KG_THREADS, smem, st>>>(a));
   } else if (a.want_x_grads) {
