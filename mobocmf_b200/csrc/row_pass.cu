@@ -1010,26 +1010,13 @@ __global__ void reduce_partials_kernel(const double* __restrict__ part, int nblo
 // A2 = sum_r w_r t_r t_r^T from the saved whitened rows T [R][MP] (the SYRK of the backward).
 // The lower triangle is cut into 32 x 32 blocks (36 at MP = 256), one block per warp, 12 warps per CTA, so every
 // DMMA is useful work and every warp carries the same load.  A CTA streams ALL MP columns of its chunk of rows
-// through a 3-stage cp.async pipeline (32 rows per stage) and each warp reads its two column panels from there.
+// through a 3-stage bulk-copy (TMA engine) + mbarrier pipeline (32 rows per stage, one 2 KB copy per row) and each
+// warp reads its two column panels from there.
 // Partial blocks per row chunk are folded in chunk order by syrk_reduce_kernel, which also mirrors the result to
 // the full symmetric matrix.  w_r = dvar_r (which = 0) or dvar_r * [clamped row] (which = 1, skipped unless some
 // row was clamped).  Group 0 also accumulates b = sum_r dmu_r t_r.
 // ---------------------------------------------------------------------------------------------------
 constexpr int SY_KB = 32, SY_WARPS = 12, SY_THREADS = SY_WARPS * 32, SY_STAGES = 3;
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz));
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  const int sz = valid ? 8 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 __host__ __device__ inline size_t syrk_stage_doubles(int MP) { return (size_t)SY_KB * (MP + 4) + 3 * SY_KB; }
 __host__ __device__ inline int syrk_nblocks(int MP) { const int nb = MP / 32; return nb * (nb + 1) / 2; }
@@ -1040,6 +1027,7 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
             const double* __restrict__ dmu, double* __restrict__ part_alpha) {
   if (which == 1 && (clamp_count == nullptr || *clamp_count == 0u)) return;
   extern __shared__ __align__(16) double sy_sh[];
+  __shared__ unsigned long long full[SY_STAGES];     // mbarriers: stage s % SY_STAGES has landed
   const int ld = MP + 4;
   const size_t stage = syrk_stage_doubles(MP);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1055,25 +1043,52 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
   const long long rend = min(R, rbeg + rows_per);
   const int nst = rend > rbeg ? (int)((rend - rbeg + SY_KB - 1) / SY_KB) : 0;
   const bool do_alpha = which == 0 && group == 0 && part_alpha != nullptr && dmu != nullptr;
-  const int vec_per_row = MP / 2;
+  const unsigned row_bytes = (unsigned)MP * sizeof(double);
+  // the three per-row arrays travel as 256-byte bulk copies when they are 16-byte aligned (always, for fresh
+  // allocations); otherwise, and for the ragged last stage, warp 0 loads them itself
+  const bool vec_ok = ((((uintptr_t)dvar) | ((uintptr_t)dmu) | ((uintptr_t)craw)) & 15) == 0;
 
+  if (tid == 0) {
+    for (int s = 0; s < SY_STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // warp 0 fills a stage: one 2 KB bulk copy per row of T (the TMA engine computes no per-element addresses: the
+  // per-thread 16-byte cp.async loop of the first version spent 14 % of the kernel's samples on index arithmetic,
+  // profiles/r01r_*), completion on the stage's mbarrier
   auto issue = [&](int s) {
-    double* Ts = sy_sh + (size_t)(s % SY_STAGES) * stage;
+    const int slot = s % SY_STAGES;
+    double* Ts = sy_sh + (size_t)slot * stage;
     double* ws = Ts + (size_t)SY_KB * ld;
     const long long r0 = rbeg + (long long)s * SY_KB;
-    for (int idx = tid; idx < SY_KB * vec_per_row; idx += SY_THREADS) {
-      const int r = idx / vec_per_row, c = (idx - r * vec_per_row) * 2;
-      const long long row = r0 + r;
-      const bool ok = row < rend;
-      cp_async16(Ts + (size_t)r * ld + c, ok ? T + (size_t)row * MP + c : T, ok);
+    const int nrow = (int)min((long long)SY_KB, rend - r0);
+    const bool bulk_small = vec_ok && nrow == SY_KB;
+    if (lane >= nrow)                                            // ragged last stage: zero rows (their weight is 0)
+      for (int j = 0; j < MP; ++j) Ts[(size_t)lane * ld + j] = 0.0;
+    if (!bulk_small) {
+      const bool ok = lane < nrow;
+      ws[lane] = (ok && dvar) ? dvar[r0 + lane] : 0.0;
+      ws[SY_KB + lane] = (ok && dmu) ? dmu[r0 + lane] : 0.0;
+      ws[2 * SY_KB + lane] = (ok && craw) ? craw[r0 + lane] : 0.0;
+    } else {
+      if (!dmu) ws[SY_KB + lane] = 0.0;
+      if (!craw) ws[2 * SY_KB + lane] = 0.0;
     }
-    if (tid < 3 * SY_KB) {
-      const int arr = tid / SY_KB, k = tid - arr * SY_KB;
-      const long long row = r0 + k;
-      const double* src = arr == 0 ? dvar : (arr == 1 ? dmu : craw);
-      const bool ok = row < rend && src != nullptr;
-      cp_async8(ws + tid, ok ? src + row : (const double*)T, ok);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses to the slot -> async writes
+    __syncwarp();
+    if (lane == 0) {
+      unsigned bytes = (unsigned)nrow * row_bytes;
+      if (bulk_small) bytes += (unsigned)SY_KB * 8u * (1u + (dmu ? 1u : 0u) + (craw ? 1u : 0u));
+      mbar_expect_tx(&full[slot], bytes);                        // release: the generic writes above are visible
+      if (bulk_small) {
+        bulk_g2s(ws, dvar + r0, SY_KB * 8u, &full[slot]);
+        if (dmu) bulk_g2s(ws + SY_KB, dmu + r0, SY_KB * 8u, &full[slot]);
+        if (craw) bulk_g2s(ws + 2 * SY_KB, craw + r0, SY_KB * 8u, &full[slot]);
+      }
     }
+    __syncwarp();
+    if (lane < nrow) bulk_g2s(Ts + (size_t)lane * ld, T + (size_t)(r0 + lane) * MP, row_bytes, &full[slot]);
   };
 
   double acc[4][4][2];
@@ -1081,18 +1096,14 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
   for (int x = 0; x < 4; ++x)
 #pragma unroll
     for (int y = 0; y < 4; ++y) { acc[x][y][0] = 0.0; acc[x][y][1] = 0.0; }
-  double al = 0.0;
+  double al[4] = {0.0, 0.0, 0.0, 0.0};
 
-  for (int s = 0; s < SY_STAGES - 1; ++s) {
-    if (s < nst) issue(s);
-    cp_async_commit();
-  }
+  if (warp == 0)
+    for (int s = 0; s < SY_STAGES && s < nst; ++s) issue(s);
   for (int it = 0; it < nst; ++it) {
-    cp_async_wait<SY_STAGES - 2>();
-    __syncthreads();   // stage `it` has landed for every thread; everyone is done with the buffer refilled below
-    if (it + SY_STAGES - 1 < nst) issue(it + SY_STAGES - 1);
-    cp_async_commit();
-    const double* Ts = sy_sh + (size_t)(it % SY_STAGES) * stage;
+    const int slot = it % SY_STAGES;
+    mbar_wait(&full[slot], (unsigned)(it / SY_STAGES) & 1u);
+    const double* Ts = sy_sh + (size_t)slot * stage;
     const double* ws = Ts + (size_t)SY_KB * ld;
     if (active) {
       const double* Ap = Ts + 32 * bi + g;
@@ -1114,11 +1125,14 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
       }
     }
     if (do_alpha && tid < MP) {
-#pragma unroll 8
-      for (int k = 0; k < SY_KB; ++k) al = fma(ws[SY_KB + k], Ts[(size_t)k * ld + tid], al);
+#pragma unroll
+      for (int k = 0; k < SY_KB; k += 4)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) al[c] = fma(ws[SY_KB + k + c], Ts[(size_t)(k + c) * ld + tid], al[c]);
     }
+    __syncthreads();   // everyone is done with this slot: refill it with the stage SY_STAGES ahead
+    if (warp == 0 && it + SY_STAGES < nst) issue(it + SY_STAGES);
   }
-  cp_async_wait<0>();
   if (active) {
     double* out = part + ((size_t)chunk * nblk + q) * 1024;
 #pragma unroll
@@ -1128,7 +1142,7 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
 #pragma unroll
         for (int e = 0; e < 2; ++e) out[(8 * x + g) * 32 + 8 * y + 2 * t + e] = acc[x][y][e];
   }
-  if (do_alpha && tid < MP) part_alpha[(size_t)chunk * MP + tid] = al;
+  if (do_alpha && tid < MP) part_alpha[(size_t)chunk * MP + tid] = (al[0] + al[1]) + (al[2] + al[3]);
 }
 
 __global__ void syrk_reduce_kernel(const double* __restrict__ part, int nchunk, int MP, double* __restrict__ A,
