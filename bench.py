@@ -216,8 +216,8 @@ def run_ours(args):
         sampler.start()                   # sampled through warm-up and the timed region (a timed region of K steps
     for _ in range(max(args.warmup, 3)):  # of 3 ms is shorter than one nvidia-smi call)
         device_step()
-    for _ in range(80):                   # ~0.25 s more under load on EVERY rank (the step holds a collective), so
-        device_step()                     # that the sampler has readings under load before the clock starts
+    for _ in range(250):                  # ~0.65 s more under load on EVERY rank (the step holds a collective), so
+        device_step()                     # that the sampler has several readings under load before the clock starts
     l0 = _lib.launch_count()
     ms = timed(device_step, args.steps)
     launches = _lib.launch_count() - l0
@@ -599,7 +599,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="fused", choices=["fused", "composable"],
