@@ -33,7 +33,11 @@ def make_model(L=3, M=48, ls=0.25, seed=1, n_per=(60, 40, 20), d=3):
 
 
 @pytest.mark.parametrize("L,S,B,M,freeze", [(3, 5, 33, 48, None), (2, 1, 40, 32, None), (3, 1, 70, 75, "phase1"),
-                                            (3, 4, 64, 64, "cond"), (2, 3, 130, 256, None)])
+                                            (3, 4, 64, 64, "cond"), (2, 3, 130, 256, None),
+                                            # 10 000 ragged rows in the upper layer: every persistent CTA of the
+                                            # product / SYRK kernels walks several tiles (prefetch pipelines, mbarrier
+                                            # phase wrap, fragment rings reused across tiles)
+                                            (2, 40, 250, 256, None)])
 def test_fused_step_matches_oracle_and_composable(L, S, B, M, freeze):
     from mobocmf_b200.fused import FusedELBOStep
     from mobocmf_b200.gp import settings
