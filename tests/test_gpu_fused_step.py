@@ -201,17 +201,20 @@ def test_training_loop_decreases_loss_and_matches_composable_loop():
     assert losses[-1] < losses[0]
 
 
-def test_fused_acquisition_chain_matches_python_path_and_oracle():
+# second case: 420 candidates x 25 samples = 10 500 rows per upper layer at M = 256: the persistent CTAs of the forward
+# kernel walk several tiles in eval mode
+@pytest.mark.parametrize("M,d,ncand,n_per", [(48, 2, 203, (60, 40, 20)), (256, 6, 420, (300, 200, 100))])
+def test_fused_acquisition_chain_matches_python_path_and_oracle(M, d, ncand, n_per):
     from mobocmf_b200.acquisition_functions.JESMOC_MFDGP import _JES_MFDGP
     L = 3
-    mu_model, x, y, fid, N = make_model(L=L, M=48, d=2)
+    mu_model, x, y, fid, N = make_model(L=L, M=M, d=d, n_per=n_per)
     mc_model = copy.deepcopy(mu_model)
     g = torch.Generator().manual_seed(9)
     with torch.no_grad():
         for n, p in mc_model.named_parameters():
             if "chol_variational_covar" in n:
                 p.mul_(0.6)
-    X = torch.rand(203, 1, 2, generator=g, dtype=torch.float64)
+    X = torch.rand(ncand, 1, d, generator=g, dtype=torch.float64)
     for fidelity in range(L):
         acq = _JES_MFDGP(fidelity, mu_model, mc_model)
         with torch.no_grad():
