@@ -397,6 +397,31 @@ def bench_small_configs(dev, steps=200):
             torch.cuda.synchronize()
             res[mode + "_us_per_step"] = round(e0.elapsed_time(e1) / steps * 1e3, 1)
         res["steps_per_s"] = round(1e6 / res["graph_us_per_step"], 1)
+        # K = 6 independent black-box models (4 objectives + 2 constraints, BASELINE.json configs[4]) trained round-robin,
+        # one CUDA stream and one graph each (BlackBoxMFDGPFitter(concurrent_models=True)): their latency-bound chains
+        # overlap on the GPU.  Wall clock between two device synchronisations.
+        K = 6
+        gsteps, streams = [], []
+        for k in range(K):
+            torch.manual_seed(k)
+            model = MFDGP(x, y, fid, 2)
+            model.double().to(dev)
+            elbo = VariationalELBOMF(model, N, 2)
+            model.fix_variational_hypers(False)
+            opt = Adam([{"params": model.parameters()}], lr=0.001, capturable=True)
+            gsteps.append(GraphedELBOStep(FusedELBOStep(model, elbo), opt, N))
+            streams.append(torch.cuda.Stream(device=dev))
+        for it in range(10 + steps):
+            if it == 10:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            for gs, st in zip(gsteps, streams):
+                with torch.cuda.stream(st):
+                    gs(xb, yb, fb)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        res["six_models_concurrent_us_per_model_step"] = round(dt / (steps * K) * 1e6, 1)
+        res["six_models_concurrent_steps_per_s"] = round(steps * K / dt, 1)
         out[name] = res
     return out
 

@@ -64,8 +64,20 @@ class RFFSample(object):
                 scales += [math.sqrt(2.0 * s["alpha_x1"] / F) * math.sqrt(s["nu_lin"]),
                            math.sqrt(2.0 * s["alpha_x1f"] / F), math.sqrt(2.0 * s["alpha_x2"] / F)]
             self._params.append(blk.to(device=self.device, dtype=torch.float64).contiguous())
-        self._scales = (ctypes.c_double * len(scales))(*scales)
-        self._ptrs = _lib.ptr_array(self._params)
+        self._scale_values = scales
+        self._scales = self._ptrs = None      # ctypes views, built on first use (not picklable / deep-copyable)
+
+    def __getstate__(self):
+        # the fitter that stores the samples is deep-copied (copy_uncond, util/blackbox_mfdgp_fitter.py:383)
+        state = self.__dict__.copy()
+        state["_scales"] = state["_ptrs"] = None
+        return state
+
+    def _ctypes_views(self):
+        if self._ptrs is None:
+            self._scales = (ctypes.c_double * len(self._scale_values))(*self._scale_values)
+            self._ptrs = _lib.ptr_array(self._params)
+        return self._ptrs, self._scales
 
     @property
     def num_layers(self):
@@ -80,8 +92,9 @@ class RFFSample(object):
         n = x.shape[0]
         f = torch.empty(self.num_layers, n, dtype=torch.float64, device=self.device)
         g = torch.empty(n, self.d, dtype=torch.float64, device=self.device) if want_grad else None
+        ptrs, scales = self._ctypes_views()
         with torch.cuda.device(self.device):
-            _lib.check(_lib.load().mobo_rff_eval(self.num_layers, self.d, self.nF, self._ptrs, self._scales,
+            _lib.check(_lib.load().mobo_rff_eval(self.num_layers, self.d, self.nF, ptrs, scales,
                                                  _lib.ptr(x), n, _lib.ptr(f), _lib.ptr(g), _lib.stream_ptr()),
                        "mobo_rff_eval")
         return f, g

@@ -68,7 +68,7 @@ class BlackBoxMFDGPFitter():
 
     def __init__(self, num_fidelities, batch_size, lr_1=0.003, lr_2=0.001, num_epochs_1=5000, num_epochs_2=15000,
                  pareto_set_size=50, opt_grid_size=1000, eps=1e-8, decoupled_evals=False,
-                 type_lengthscale=TL.MEDIAN, device=None, use_cuda_graph=False):
+                 type_lengthscale=TL.MEDIAN, device=None, use_cuda_graph=False, concurrent_models=False):
         self.num_obj = 0
         self.num_con = 0
         self.models_uncond_trained = False
@@ -92,6 +92,11 @@ class BlackBoxMFDGPFitter():
         # one CUDA-graph launch per step instead of ~55 kernel launches: the regime of the reference's examples
         # (full batch, M = N of a few tens) is launch-latency bound
         self.use_cuda_graph = use_cuda_graph
+        # the black boxes' MFDGPs are independent during unconditioned training (fitter.py:134-152 loops over them):
+        # with concurrent_models their steps are enqueued round-robin on one CUDA stream each, so the latency-bound
+        # kernel chains of the K models overlap on the GPU (the reference trains them one after the other; the order
+        # in which the models consume torch's random stream changes, their distribution does not)
+        self.concurrent_models = concurrent_models
         self.pareto_set = None
         self.pareto_front = None
         self.verbose = True
@@ -181,13 +186,31 @@ class BlackBoxMFDGPFitter():
             for h in handlers.values():
                 h.mfdgp.fix_variational_hypers(fix_variational_hypers)
                 opts.append(Adam([{'params': h.mfdgp.parameters()}], lr=lr, capturable=self.use_cuda_graph))
-            for n, (h, optimizer) in enumerate(zip(handlers.values(), opts)):
+            hs = list(handlers.values())
+
+            def report(n, i, loss_iter, kl_iter):
+                if self.verbose and ((i % ITER_PRINT) == 0 or ((i + 1) == num_epochs)):
+                    print("[%s: " % kind, n, "] Epoch:", i, "/", num_epochs, ". Avg. Neg. ELBO per epoch:",
+                          loss_iter.item(), "\t KL per epoch:", kl_iter.item())
+                    sys.stdout.flush()
+
+            if self.concurrent_models and len(hs) > 1:
+                cur = torch.cuda.current_stream(hs[0].device)
+                streams = [torch.cuda.Stream(device=h.device) for h in hs]
+                for st in streams:
+                    st.wait_stream(cur)
+                for i in range(num_epochs):
+                    for n, (h, optimizer, st) in enumerate(zip(hs, opts, streams)):
+                        with torch.cuda.stream(st):
+                            loss_iter, kl_iter = func_update_model(h.mfdgp, h.elbo, optimizer, h.train_loader)
+                            report(n, i, loss_iter, kl_iter)
+                for st in streams:
+                    cur.wait_stream(st)
+                continue
+            for n, (h, optimizer) in enumerate(zip(hs, opts)):
                 for i in range(num_epochs):
                     loss_iter, kl_iter = func_update_model(h.mfdgp, h.elbo, optimizer, h.train_loader)
-                    if self.verbose and ((i % ITER_PRINT) == 0 or ((i + 1) == num_epochs)):
-                        print("[%s: " % kind, n, "] Epoch:", i, "/", num_epochs, ". Avg. Neg. ELBO per epoch:",
-                              loss_iter.item(), "\t KL per epoch:", kl_iter.item())
-                        sys.stdout.flush()
+                    report(n, i, loss_iter, kl_iter)
 
     def train_mfdgps(self):
         self._train_mfdgp(self._update_model, fix_variational_hypers=True, num_epochs=self.num_epochs_1,

@@ -12,15 +12,16 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("use_cuda_graph", [False, True])
-def test_forrester_fit_condition_acquire(use_cuda_graph):
+@pytest.mark.parametrize("use_cuda_graph,concurrent", [(False, False), (True, False), (True, True)])
+def test_forrester_fit_condition_acquire(use_cuda_graph, concurrent):
     from mobocmf_b200.acquisition_functions.JESMOC_MFDGP import JESMOC_MFDGP
     from mobocmf_b200.util.blackbox_mfdgp_fitter import BlackBoxMFDGPFitter
     x, ys, fid = forrester_data()
     L, N = 2, x.shape[0]
     torch.manual_seed(0)
     fitter = BlackBoxMFDGPFitter(L, N, num_epochs_1=40, num_epochs_2=40, device=torch.device(DEV),
-                                 use_cuda_graph=use_cuda_graph)
+                                 use_cuda_graph=use_cuda_graph, concurrent_models=concurrent, pareto_set_size=6,
+                                 opt_grid_size=150)
     fitter.verbose = False
     fitter.initialize_mfdgp(x, ys["obj1"], fid, "obj1")
     fitter.initialize_mfdgp(x, ys["obj2"], fid, "obj2")
@@ -36,10 +37,19 @@ def test_forrester_fit_condition_acquire(use_cuda_graph):
     if use_cuda_graph:
         assert any(getattr(hh.elbo, "_fused_step", None) and getattr(hh.elbo._fused_step, "_graphs", None)
                    for hh in fitter.mfdgp_handlers_objs.values())
-    # Pareto-set sampling (RFF + MOOP) is out of the hot path: provide a Pareto set / front
-    g = torch.Generator().manual_seed(1)
-    fitter.pareto_set = torch.rand(6, 1, generator=g, dtype=torch.float64)
-    fitter.pareto_front = torch.randn(6, 2, generator=g, dtype=torch.float64) * 0.3
+    if concurrent:
+        # the three models trained on their own streams: every one of them moved and stayed finite
+        for hh in list(fitter.mfdgp_handlers_objs.values()) + list(fitter.mfdgp_handlers_cons.values()):
+            assert all(bool(torch.isfinite(p).all()) for p in hh.mfdgp.parameters())
+        # Pareto set by RFF function samples + MOOP (fitter.py:181-225) on the GPU
+        import numpy as np
+        np.random.seed(4)
+        pset, pfront, _, _ = fitter.sample_and_store_pareto_solution()
+        assert pset.shape[1] == 1 and pfront.shape == (pset.shape[0], 2) and 1 <= pset.shape[0] <= 6
+    else:
+        g = torch.Generator().manual_seed(1)
+        fitter.pareto_set = torch.rand(6, 1, generator=g, dtype=torch.float64)
+        fitter.pareto_front = torch.randn(6, 2, generator=g, dtype=torch.float64) * 0.3
     fitter.num_epochs_2 = 15
     bounds = torch.tensor([[0.0], [1.0]], dtype=torch.float64, device=DEV)
     acq = JESMOC_MFDGP(model=fitter, num_fidelities=L, standard_bounds=bounds)

@@ -41,6 +41,9 @@ def test_rff_eval_reproduces_reference(name, mode):
     assert rel(gb.cpu().numpy(), g[mode + "_g1"]) < 1e-12
     s0 = to_sample(golden_chain(g, mode)[:1], d)
     assert rel(s0(g["xg"][0], gradient=True), g[mode + "_g0"][0]) < 1e-12
+    import copy
+    s2 = copy.deepcopy(s)                       # the fitter holding the samples is deep-copied (copy_uncond)
+    assert rel(s2(g["X"]), g[mode + "_f1"]) < 1e-12
 
 
 @pytest.mark.parametrize("d,L,F,n", [(6, 3, 500, 4099), (1, 2, 37, 33), (8, 4, 64, 257)])
