@@ -377,8 +377,9 @@ def bench_small_configs(dev, steps=200):
             opt = Adam([{"params": model.parameters()}], lr=0.001, capturable=(mode == "graph"))
             fstep = FusedELBOStep(model, elbo)
             xd, yd, fd = x.to(dev), y.to(dev), fid.to(dev)
-            perm = torch.randperm(N, device=dev)
-            xb, yb, fb = xd[perm], yd[perm], fd[perm]
+            perm = torch.randperm(N)
+            xb, yb, fb = xd[perm.to(dev)], yd[perm.to(dev)], fd[perm.to(dev)]
+            xb._mobo_host = x[perm]          # what the fitter's loader attaches: the Q4 test runs on the host
             if mode == "graph":
                 gstep = GraphedELBOStep(fstep, opt, N)
                 fn = lambda: gstep(xb, yb, fb)

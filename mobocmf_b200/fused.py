@@ -169,7 +169,16 @@ class FusedELBOStep(object):
     def applies(self, x_batch):
         """False when the minibatch equals the inducing inputs row for row: upstream then short-cuts layer 0 to
         N(m, S) (quirk Q4), which only the composable path reproduces.  Costs a device sync only when B == M."""
-        return not (x_batch.shape[0] == self.M and bool(torch.equal(x_batch, self.layers[0]._Zx())))
+        if x_batch.shape[0] != self.M:
+            return True
+        Z = self.layers[0]._Zx()
+        host = getattr(x_batch, "_mobo_host", None)       # host copy attached by the fitter's loader: no sync
+        if host is not None:
+            key = (Z.data_ptr(), Z._version)
+            if getattr(self, "_z_host_key", None) != key:
+                self._z_host, self._z_host_key = Z.detach().cpu(), key
+            return not bool(torch.equal(host, self._z_host))
+        return not bool(torch.equal(x_batch, Z))
 
     # ---- the step ---------------------------------------------------------------------------------------------
     def __call__(self, x_batch, y_batch, fidelities, eps=None, num_samples=1, accumulate=False, check_shortcut=True):

@@ -32,13 +32,22 @@ class _Loader(object):
 
     def __init__(self, x, y, f, batch_size, shuffle=True):
         self.x, self.y, self.f, self.batch_size, self.shuffle = x, y, f, batch_size, shuffle
+        # small data sets (the reference's own configurations): a host copy of x, so that the "batch equals the
+        # inducing inputs" test of the fused step (quirk Q4) is answered on the host instead of by a device
+        # synchronisation in every step
+        self.x_host = x.detach().cpu() if x.shape[0] <= 4096 else None
 
     def __iter__(self):
         n = self.x.shape[0]
-        perm = torch.randperm(n, device=self.x.device) if self.shuffle else torch.arange(n, device=self.x.device)
+        # the permutation comes from torch's CPU generator, like the reference's DataLoader(shuffle=True)
+        perm_host = torch.randperm(n) if self.shuffle else torch.arange(n)
+        perm = perm_host.to(self.x.device)
         for i in range(0, n, self.batch_size):
             idx = perm[i:i + self.batch_size]
-            yield self.x[idx], self.y[idx], self.f[idx]
+            xb = self.x[idx]
+            if self.x_host is not None:
+                xb._mobo_host = self.x_host[perm_host[i:i + self.batch_size]]
+            yield xb, self.y[idx], self.f[idx]
 
 
 class MFDGPHandler():
