@@ -321,6 +321,22 @@ class MFDGPHiddenLayer(nn.Module):
         return F.layer_rows(ops, theta, zf, self._Zx(), x, mu_prev, var_prev, eps, f_direct, kind=self.kind,
                             xrep=xrep, prep=prep, eps_mod=eps_mod, R=R, training=self.training)
 
+    def _equals_inducing(self, x):
+        """x equals this layer's inducing inputs row for row (the upstream `torch.equal(x, Z)` shortcut, quirk Q4).
+        A device comparison costs a synchronisation; callers that know the answer on the host say so: the fitter's
+        loader attaches a host copy (`x._mobo_host`), the graph-captured conditioned step marks its static buffers
+        (`x._mobo_not_z`) after checking every minibatch on the host."""
+        Zx = self._Zx()
+        if x.shape != Zx.shape or getattr(x, "_mobo_not_z", False):
+            return False
+        host = getattr(x, "_mobo_host", None)
+        if host is not None:
+            key = ("Zx_host", Zx.data_ptr(), Zx._version)
+            if self._dev_cache.get("Zx_host_key") != key:
+                self._dev_cache["Zx_host"], self._dev_cache["Zx_host_key"] = Zx.detach().cpu(), key
+            return bool(torch.equal(host, self._dev_cache["Zx_host"]))
+        return bool(torch.equal(x, Zx))
+
     def forward(self, x):
         raise RuntimeError("MFDGPHiddenLayer.forward (the lazy prior over cat[Z, X]) has no dense counterpart here; "
                            "call the layer")
@@ -330,8 +346,7 @@ class MFDGPHiddenLayer(nn.Module):
         (layer 0, leading num_likelihood_samples dim, quirk Q3), (R,) otherwise."""
         if len(other_inputs) == 0:
             assert x.shape[-1] == self.input_dims
-            Zx = self._Zx()
-            if x.shape == Zx.shape and self.num_layer == 0 and bool(torch.equal(x, Zx)):
+            if self.num_layer == 0 and self._equals_inducing(x):
                 q = self.variational_strategy.variational_distribution        # quirk Q4 shortcut: N(m, S)
                 mu, var = q.mean, q.raw_variance
             else:

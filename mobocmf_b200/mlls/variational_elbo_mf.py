@@ -22,17 +22,19 @@ class VariationalELBOMF(object):
         num_batch = target.shape[1]
         data_term = 0.0
         for i in range(self.num_fidelities):
+            # the reference tests `mask.sum() != 0` and sums `ell[mask]` (variational_elbo_mf.py:33-38): both force a
+            # device synchronisation (and a data-dependent shape); the masked sum below is the same number, adds an
+            # exact zero for a fidelity without points, and can be captured in a CUDA graph
             mask = fidelities.T == i
-            if mask.sum() != 0:
-                likelihood = getattr(self.model, self.model.name_hidden_layer_likelihood + str(i))
-                dist = l_approximate_dist_f[i]
-                S = getattr(dist, "samples_per_point", 1)
-                if S > 1:   # S-sample extension: average the per-sample terms of each point
-                    ell = likelihood.expected_log_prob(target.reshape(-1, 1).expand(-1, S).reshape(-1), dist)
-                    ell = ell.reshape(-1, S).mean(1)[None, :]
-                else:
-                    ell = likelihood.expected_log_prob(target, dist)
-                data_term = data_term + ell[mask].sum()
+            likelihood = getattr(self.model, self.model.name_hidden_layer_likelihood + str(i))
+            dist = l_approximate_dist_f[i]
+            S = getattr(dist, "samples_per_point", 1)
+            if S > 1:   # S-sample extension: average the per-sample terms of each point
+                ell = likelihood.expected_log_prob(target.reshape(-1, 1).expand(-1, S).reshape(-1), dist)
+                ell = ell.reshape(-1, S).mean(1)[None, :]
+            else:
+                ell = likelihood.expected_log_prob(target, dist)
+            data_term = data_term + torch.where(mask, ell, torch.zeros((), dtype=ell.dtype, device=ell.device)).sum()
         if include_kl_term is False:
             return data_term
         kl_divergence = self.model.variational_strategy.kl_divergence()

@@ -23,6 +23,19 @@ from .moop import MOOP, NotFeasiblePoints
 ITER_PRINT = 1000
 
 
+def _prod(t, dim):
+    """torch.prod(t, dim) as a chain of multiplications: the derivative of torch.prod reads a zero count back to the
+    host (a device synchronisation in every backward, and illegal inside a CUDA-graph capture); the chain has the same
+    derivative, zeros included, and the reduced dimension is a handful of black boxes."""
+    parts = torch.unbind(t, dim)
+    if len(parts) == 0:
+        return torch.ones(t.shape[:dim] + t.shape[dim + 1:], dtype=t.dtype, device=t.device)
+    out = parts[0]
+    for q in parts[1:]:
+        out = out * q
+    return out
+
+
 def _normal_cdf(x):
     return 0.5 * (1.0 + torch.erf(x / np.sqrt(2.0)))
 
@@ -71,6 +84,115 @@ class MFDGPHandler():
         self.iter_train_loader = None
         self.num_data = x_train.shape[0]
         self.num_fidelities = num_fidelities
+
+
+class _GraphedConditionedStep(object):
+    """One conditioned iteration (``_update_conditioned_models``, fitter.py:272-354: three MFDGP forwards per black
+    box — minibatch, Pareto set, x-tilde —, the theta / omega factors, backward, Adam) captured ONCE in a CUDA graph
+    and replayed per iteration.  At the reference's sizes the iteration is a few hundred small kernels and ~13 ms of
+    Python / autograd dispatch when enqueued eagerly; a replay is one launch.  The minibatches are staged into static
+    buffers, x-tilde and the training normals are drawn inside the graph by torch's graph-safe generator.  An
+    iteration whose minibatch equals the inducing inputs (quirk Q4 changes the arithmetic) runs eagerly."""
+
+    def __init__(self, fitter, handlers_objs, handlers_cons, optimizer, warmup=2):
+        self.fitter, self.optimizer, self.warmup = fitter, optimizer, warmup
+        self.hs_o, self.hs_c = list(handlers_objs), list(handlers_cons)
+        self.keys = [("obj", i) for i in range(len(self.hs_o))] + [("con", k) for k in range(len(self.hs_c))]
+        self.handlers = self.hs_o + self.hs_c
+        dev = self.handlers[0].device
+        # everything the iteration reads must already live on the device: a host-to-device copy cannot be captured
+        fitter.pareto_set = fitter.pareto_set.to(dev)
+        fitter.pareto_front = fitter.pareto_front.to(dev)
+        fitter.thresholds_cons = fitter.thresholds_cons.to(dev)
+        self.x_tilde = torch.zeros(10, fitter.pareto_set.shape[1], dtype=torch.float64, device=dev)
+        self.static = None
+        self.graph = None
+        self.loss = None
+
+    def _fetch(self):
+        out = {}
+        for key, h in zip(self.keys, self.handlers):
+            try:
+                out[key] = next(h.iter_train_loader)
+            except Exception:
+                h.iter_train_loader = iter(h.train_loader)
+                out[key] = next(h.iter_train_loader)
+        return out
+
+    def _hits_shortcut(self, batches):
+        for key, h in zip(self.keys, self.handlers):
+            if getattr(h.mfdgp, h.mfdgp.name_hidden_layer + "0")._equals_inducing(batches[key][0]):
+                return True
+        return False
+
+    def _stage(self, batches):
+        if self.static is None:
+            self.static = {}
+            for key in self.keys:
+                bufs = tuple(t.detach().clone() for t in batches[key])
+                bufs[0]._mobo_not_z = True          # checked on the host for every minibatch (_hits_shortcut)
+                self.static[key] = bufs
+            return
+        for key in self.keys:
+            for dst, src in zip(self.static[key], batches[key]):
+                if dst.shape != src.shape:
+                    raise RuntimeError("the captured conditioned step needs minibatches of constant shape")
+                dst.copy_(src)
+
+    def _iteration(self):
+        self.x_tilde.uniform_()
+        loss = self.fitter.conditioned_loss(self.hs_o, self.hs_c, x_tilde=self.x_tilde, batches=self.static)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def _layers(self):
+        for h in self.handlers:
+            m = h.mfdgp
+            for i in range(m.num_hidden_layers):
+                yield getattr(m, m.name_hidden_layer + str(i))
+
+    def _capture(self):
+        params = [p for g in self.optimizer.param_groups for p in g["params"]]
+        snap = [p.detach().clone() for p in params]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                self.optimizer.zero_grad(set_to_none=True)
+                self._iteration()
+        torch.cuda.current_stream().wait_stream(side)
+        self.optimizer.zero_grad(set_to_none=True)
+        for layer in self._layers():
+            layer._ops_cache = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._iteration()
+        with torch.no_grad():       # warm-up and capture do not count as training iterations
+            for p, v in zip(params, snap):
+                p.copy_(v)
+            for p in params:
+                st = self.optimizer.state.get(p)
+                if st:
+                    st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+            if self.optimizer._step_dev is not None:
+                self.optimizer._step_dev.zero_()
+
+    def __call__(self):
+        batches = self._fetch()
+        if self._hits_shortcut(batches):
+            self.optimizer.zero_grad()
+            loss = self.fitter.conditioned_loss(self.hs_o, self.hs_c, batches=batches)
+            loss.backward()
+            self.optimizer.step()
+            return loss.detach()
+        self._stage(batches)
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        for layer in self._layers():
+            layer._ops_cache = None       # the cached operators belong to the graph's memory pool
+        return self.loss
 
 
 class BlackBoxMFDGPFitter():
@@ -269,7 +391,7 @@ class BlackBoxMFDGPFitter():
         thr = self.thresholds_cons.to(cs_mean.device)
         gamma_c = (cs_mean - thr[:, None]) / torch.sqrt(cs_var)
         gamma_f_star = (pareto_front[:, :, None] - fs_mean) / torch.sqrt(fs_var)
-        prod = torch.prod(_normal_cdf(gamma_c), 0) * torch.prod(_normal_cdf(gamma_f_star), 1)
+        prod = _prod(_normal_cdf(gamma_c), 0) * _prod(_normal_cdf(gamma_f_star), 1)
         return torch.sum(np.log(self.eps) * prod + np.log(1 - self.eps) * (1.0 - prod))
 
     # ---- the conditioned step (fitter.py:272-346) ----
@@ -297,33 +419,41 @@ class BlackBoxMFDGPFitter():
         def e(key, which):
             return None if eps is None else eps[key][which]
 
-        for i, h in enumerate(handlers_objs):
-            key = ("obj", i)
+        # The black boxes' models are coupled only through the omega factors below: the three forwards of each of them
+        # (minibatch, Pareto set, x-tilde) run on the model's own stream, forked from and joined back into the current
+        # one, so their kernel chains overlap (also as parallel branches of the captured graph, and again in the
+        # backward, which autograd runs on the streams of the forward).
+        cur = torch.cuda.current_stream(dev)
+        nmodels = len(handlers_objs) + len(handlers_cons)
+        streams = self.__dict__.setdefault("_cond_streams", [])
+        while len(streams) < nmodels:
+            streams.append(torch.cuda.Stream(device=dev))
+        terms, fm, fv, cm, cv = [], [], [], [], []
+        for n, (kind, i, h) in enumerate([("obj", i, h) for i, h in enumerate(handlers_objs)] +
+                                         [("con", k, h) for k, h in enumerate(handlers_cons)]):
+            key = (kind, i)
             x_batch, y_batch, fidelities = next_batch(h, key)
-            with settings.num_likelihood_samples(1):
+            st = streams[n] if nmodels > 1 else cur
+            st.wait_stream(cur)
+            with torch.cuda.stream(st), settings.num_likelihood_samples(1):
                 output = h.mfdgp(x_batch, eps=e(key, "batch"))
-                loss = loss + -h.elbo(output, y_batch.T, fidelities)[0] / x_batch.shape[0] * h.num_data
-                output = h.mfdgp(pareto_set, eps=e(key, "pareto"))
-                pareto_fidelities = torch.ones(size=(pareto_front.shape[0], 1), device=dev) * (h.num_fidelities - 1)
-                loss = loss + -h.elbo(output, pareto_front[:, i:(i + 1)].T, pareto_fidelities,
-                                      include_kl_term=False)
-        for k, h in enumerate(handlers_cons):
-            key = ("con", k)
-            x_batch, y_batch, fidelities = next_batch(h, key)
-            with settings.num_likelihood_samples(1):
-                output = h.mfdgp(x_batch, eps=e(key, "batch"))
-                loss = loss + -h.elbo(output, y_batch.T, fidelities)[0] / x_batch.shape[0] * h.num_data
-                output = h.mfdgp(pareto_set, eps=e(key, "pareto"))[h.num_fidelities - 1]
-                loss = loss + -self.loss_theta_factors(output.mean, output.variance, thr[k])
-        fm, fv, cm, cv = [], [], [], []
-        for i, h in enumerate(handlers_objs):
-            with settings.num_likelihood_samples(1):
-                output = h.mfdgp(x_tilde, eps=e(("obj", i), "tilde"))[h.num_fidelities - 1]
-            fm.append(output.mean[None, :]); fv.append(output.variance[None, :])
-        for k, h in enumerate(handlers_cons):
-            with settings.num_likelihood_samples(1):
-                output = h.mfdgp(x_tilde, eps=e(("con", k), "tilde"))[h.num_fidelities - 1]
-            cm.append(output.mean[None, :]); cv.append(output.variance[None, :])
+                t_batch = -h.elbo(output, y_batch.T, fidelities)[0] / x_batch.shape[0] * h.num_data
+                if kind == "obj":
+                    output = h.mfdgp(pareto_set, eps=e(key, "pareto"))
+                    pareto_fidelities = torch.ones(size=(pareto_front.shape[0], 1), device=dev) * \
+                        (h.num_fidelities - 1)
+                    t_pareto = -h.elbo(output, pareto_front[:, i:(i + 1)].T, pareto_fidelities, include_kl_term=False)
+                else:
+                    output = h.mfdgp(pareto_set, eps=e(key, "pareto"))[h.num_fidelities - 1]
+                    t_pareto = -self.loss_theta_factors(output.mean, output.variance, thr[i])
+                output = h.mfdgp(x_tilde, eps=e(key, "tilde"))[h.num_fidelities - 1]
+                (fm if kind == "obj" else cm).append(output.mean[None, :])
+                (fv if kind == "obj" else cv).append(output.variance[None, :])
+                terms.append(t_batch + t_pareto)
+        for n in range(nmodels if nmodels > 1 else 0):
+            cur.wait_stream(streams[n])
+        for t in terms:
+            loss = loss + t
         z = torch.zeros(0, x_tilde.shape[0], dtype=torch.double, device=dev)
         loss = loss + -self.loss_omega_factors(torch.cat(fm, 0) if fm else z, torch.cat(fv, 0) if fv else z,
                                                torch.cat(cm, 0) if cm else z, torch.cat(cv, 0) if cv else z,
@@ -331,6 +461,12 @@ class BlackBoxMFDGPFitter():
         return loss
 
     def _update_conditioned_models(self, handlers_objs, handlers_cons, optimizer):
+        if self.use_cuda_graph and getattr(optimizer, "capturable", False):
+            cache = self.__dict__.setdefault("_cond_graphs", {})
+            if id(optimizer) not in cache:
+                cache.clear()
+                cache[id(optimizer)] = _GraphedConditionedStep(self, handlers_objs, handlers_cons, optimizer)
+            return cache[id(optimizer)]()
         optimizer.zero_grad()
         loss = self.conditioned_loss(handlers_objs, handlers_cons)
         loss.backward()
@@ -342,7 +478,7 @@ class BlackBoxMFDGPFitter():
         for h in list(self.mfdgp_handlers_objs.values()) + list(self.mfdgp_handlers_cons.values()):
             h.mfdgp.fix_variational_hypers_cond(fix_variational_hypers)
             params = params + list(h.mfdgp.parameters())
-        optimizer = Adam([{'params': params}], lr=lr)
+        optimizer = Adam([{'params': params}], lr=lr, capturable=self.use_cuda_graph)
         for i in range(num_iters):
             loss_iter = func_update_model(self.mfdgp_handlers_objs.values(), self.mfdgp_handlers_cons.values(),
                                           optimizer)
@@ -367,7 +503,11 @@ class BlackBoxMFDGPFitter():
         for h in handlers:
             h.mfdgp.eval()
             h.iter_train_loader = None
+        graphs = self.__dict__.pop("_cond_graphs", None)      # captured CUDA graphs / streams do not travel through
+        self.__dict__.pop("_cond_streams", None)              # deepcopy
         self_copy = deepcopy(self)
+        if graphs is not None:
+            self._cond_graphs = graphs
         for h in handlers:
             h.mfdgp.train()
         for h in list(self_copy.mfdgp_handlers_objs.values()) + list(self_copy.mfdgp_handlers_cons.values()):
