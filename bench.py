@@ -423,7 +423,46 @@ def bench_small_configs(dev, steps=200):
         dt = time.perf_counter() - t0
         res["six_models_concurrent_us_per_model_step"] = round(dt / (steps * K) * 1e6, 1)
         res["six_models_concurrent_steps_per_s"] = round(steps * K / dt, 1)
+        if name.startswith("C2"):
+            res["conditioned_iteration_ms"] = bench_conditioned(dev, x, y, fid)
         out[name] = res
+    return out
+
+
+def bench_conditioned(dev, x, y, fid, iters=100):
+    """One conditioned iteration (_update_conditioned_models, mobocmf/util/blackbox_mfdgp_fitter.py:272-354) at the
+    Forrester size with 2 objectives + 1 constraint and a 50-point Pareto set: enqueued eagerly vs replayed as one CUDA
+    graph.  Wall clock between device synchronisations."""
+    from mobocmf_b200.fused import Adam
+    from mobocmf_b200.util.blackbox_mfdgp_fitter import BlackBoxMFDGPFitter
+    out = {}
+    for mode, use_graph in (("eager", False), ("graph", True)):
+        torch.manual_seed(0)
+        fitter = BlackBoxMFDGPFitter(2, x.shape[0], num_epochs_1=3, num_epochs_2=3, device=dev, use_cuda_graph=use_graph)
+        fitter.verbose = False
+        fitter.initialize_mfdgp(x, y, fid, "obj1")
+        fitter.initialize_mfdgp(x, -y, fid, "obj2")
+        fitter.initialize_mfdgp(x, torch.sin(7.85 * x), fid, "con1", threshold_constraint=0.0, is_constraint=True)
+        fitter.train_mfdgps()
+        g = torch.Generator().manual_seed(1)
+        fitter.pareto_set = torch.rand(50, x.shape[1], generator=g, dtype=torch.float64)
+        fitter.pareto_front = torch.randn(50, 2, generator=g, dtype=torch.float64) * 0.3
+        cond = fitter.copy_uncond()
+        cond.pareto_set, cond.pareto_front = fitter.pareto_set, fitter.pareto_front
+        cond.verbose = False
+        hs = (cond.mfdgp_handlers_objs.values(), cond.mfdgp_handlers_cons.values())
+        params = [p for h in list(hs[0]) + list(hs[1]) for p in h.mfdgp.parameters()]
+        for h in list(hs[0]) + list(hs[1]):
+            h.mfdgp.fix_variational_hypers_cond(True)
+        opt = Adam([{"params": params}], lr=1e-3, capturable=use_graph)
+        for _ in range(5):
+            cond._update_conditioned_models(hs[0], hs[1], opt)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            cond._update_conditioned_models(hs[0], hs[1], opt)
+        torch.cuda.synchronize()
+        out[mode] = round((time.perf_counter() - t0) / iters * 1e3, 3)
     return out
 
 
