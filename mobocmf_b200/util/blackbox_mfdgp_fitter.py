@@ -425,30 +425,50 @@ class BlackBoxMFDGPFitter():
         # backward, which autograd runs on the streams of the forward).
         cur = torch.cuda.current_stream(dev)
         nmodels = len(handlers_objs) + len(handlers_cons)
+        if not self.__dict__.get("_cond_streams"):
+            # gradients produced on the models' streams are accumulated into parameters that live on the current one:
+            # intended (autograd synchronises the streams), so the advisory warning about it is switched off
+            quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+            if quiet is not None:
+                quiet(False)
         streams = self.__dict__.setdefault("_cond_streams", [])
         while len(streams) < nmodels:
             streams.append(torch.cuda.Stream(device=dev))
+        sub = self.__dict__.setdefault("_cond_substreams", [])
+        while len(sub) < 2 * nmodels:
+            sub.append(torch.cuda.Stream(device=dev))
         terms, fm, fv, cm, cv = [], [], [], [], []
         for n, (kind, i, h) in enumerate([("obj", i, h) for i, h in enumerate(handlers_objs)] +
                                          [("con", k, h) for k, h in enumerate(handlers_cons)]):
             key = (kind, i)
             x_batch, y_batch, fidelities = next_batch(h, key)
             st = streams[n] if nmodels > 1 else cur
+            s_par, s_til = sub[2 * n], sub[2 * n + 1]
             st.wait_stream(cur)
             with torch.cuda.stream(st), settings.num_likelihood_samples(1):
+                # the operator chains of the model once, then its three row passes side by side
+                for l in range(h.mfdgp.num_hidden_layers):
+                    getattr(h.mfdgp, h.mfdgp.name_hidden_layer + str(l)).operators()
+                s_par.wait_stream(st)
+                s_til.wait_stream(st)
                 output = h.mfdgp(x_batch, eps=e(key, "batch"))
                 t_batch = -h.elbo(output, y_batch.T, fidelities)[0] / x_batch.shape[0] * h.num_data
-                if kind == "obj":
-                    output = h.mfdgp(pareto_set, eps=e(key, "pareto"))
-                    pareto_fidelities = torch.ones(size=(pareto_front.shape[0], 1), device=dev) * \
-                        (h.num_fidelities - 1)
-                    t_pareto = -h.elbo(output, pareto_front[:, i:(i + 1)].T, pareto_fidelities, include_kl_term=False)
-                else:
-                    output = h.mfdgp(pareto_set, eps=e(key, "pareto"))[h.num_fidelities - 1]
-                    t_pareto = -self.loss_theta_factors(output.mean, output.variance, thr[i])
-                output = h.mfdgp(x_tilde, eps=e(key, "tilde"))[h.num_fidelities - 1]
-                (fm if kind == "obj" else cm).append(output.mean[None, :])
-                (fv if kind == "obj" else cv).append(output.variance[None, :])
+                with torch.cuda.stream(s_par):
+                    if kind == "obj":
+                        output = h.mfdgp(pareto_set, eps=e(key, "pareto"))
+                        pareto_fidelities = torch.ones(size=(pareto_front.shape[0], 1), device=dev) * \
+                            (h.num_fidelities - 1)
+                        t_pareto = -h.elbo(output, pareto_front[:, i:(i + 1)].T, pareto_fidelities,
+                                           include_kl_term=False)
+                    else:
+                        output = h.mfdgp(pareto_set, eps=e(key, "pareto"))[h.num_fidelities - 1]
+                        t_pareto = -self.loss_theta_factors(output.mean, output.variance, thr[i])
+                with torch.cuda.stream(s_til):
+                    output = h.mfdgp(x_tilde, eps=e(key, "tilde"))[h.num_fidelities - 1]
+                    (fm if kind == "obj" else cm).append(output.mean[None, :])
+                    (fv if kind == "obj" else cv).append(output.variance[None, :])
+                st.wait_stream(s_par)
+                st.wait_stream(s_til)
                 terms.append(t_batch + t_pareto)
         for n in range(nmodels if nmodels > 1 else 0):
             cur.wait_stream(streams[n])
@@ -505,6 +525,7 @@ class BlackBoxMFDGPFitter():
             h.iter_train_loader = None
         graphs = self.__dict__.pop("_cond_graphs", None)      # captured CUDA graphs / streams do not travel through
         self.__dict__.pop("_cond_streams", None)              # deepcopy
+        self.__dict__.pop("_cond_substreams", None)
         self_copy = deepcopy(self)
         if graphs is not None:
             self._cond_graphs = graphs
