@@ -216,7 +216,7 @@ def run_ours(args):
         sampler.start()                   # sampled through warm-up and the timed region (a timed region of K steps
     for _ in range(max(args.warmup, 3)):  # of 3 ms is shorter than one nvidia-smi call)
         device_step()
-    for _ in range(250):                  # ~0.65 s more under load on EVERY rank (the step holds a collective), so
+    for _ in range(400):                  # ~1 s more under load on EVERY rank (the step holds a collective), so
         device_step()                     # that the sampler has several readings under load before the clock starts
     l0 = _lib.launch_count()
     ms = timed(device_step, args.steps)
