@@ -1166,15 +1166,29 @@ __global__ void syrk_reduce_kernel(const double* __restrict__ part, int nchunk, 
 // ---------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
+// per-device state (a process normally drives one GPU, but nothing here may assume it)
+constexpr int kMaxDevices = 64;
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & (kMaxDevices - 1);
+}
 static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  static int sms[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (sms[dev] == 0) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
   }
-  return g_num_sms;
+  return sms[dev];
+}
+// true the first time it is called with this flag array on the current device (dynamic shared-memory opt-in is a
+// per-device function attribute)
+static bool first_on_device(bool (&done)[kMaxDevices]) {
+  const int dev = current_device();
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
 }
 
 int row_grid(long long R) {
@@ -1186,11 +1200,9 @@ int row_grid(long long R) {
 int launch_row_fwd(const RowArgs& a, cudaStream_t st) {
   if (a.MP % 32 != 0 || a.MP > MAX_MP || a.d > kMaxD || a.M > a.MP) return -2;
   const size_t smem = row_smem_bytes(a.MP);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {false};
+  if (first_on_device(attr_done))
     cudaFuncSetAttribute(row_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes(MAX_MP));
-    attr_done = true;
-  }
   if (a.R <= 0) return 0;
   MOBO_LAUNCH("row_fwd_kernel", st, row_fwd_kernel<<<row_grid(a.R), ROW_THREADS, smem, st>>>(a));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -1218,13 +1230,12 @@ int row_bwd_grid(long long R, int reserve) {
 
 int launch_row_bwd(const RowArgs& a, cudaStream_t st) {
   if (a.MP % 32 != 0 || a.MP > MAX_MP || a.d > kMaxD || a.M > a.MP) return -2;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {false};
+  if (first_on_device(attr_done)) {
     cudaFuncSetAttribute(row_bwd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(MAX_MP));
     cudaFuncSetAttribute(kgrad_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg_smem_bytes());
     cudaFuncSetAttribute(kgrad_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg_smem_bytes());
     cudaFuncSetAttribute(kgrad_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg_smem_bytes());
-    attr_done = true;
   }
   if (a.R <= 0) return 0;
   if (((uintptr_t)a.Tsave | (uintptr_t)a.Usave) & 15) return -2;   // bulk copies need 16-byte aligned rows
@@ -1268,12 +1279,10 @@ int launch_syrk_main(const double* K, const double* dvar, const double* craw, in
                      cudaStream_t st) {
   const int nc = syrk_nchunk(MP, R);
   const size_t smem = SY_STAGES * syrk_stage_doubles(MP) * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {false};
+  if (first_on_device(attr_done))
     cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(SY_STAGES * syrk_stage_doubles(MAX_MP) * sizeof(double)));
-    attr_done = true;
-  }
   dim3 grid(syrk_ngroups(MP), nc);
   MOBO_LAUNCH("syrk_kernel", st, syrk_kernel<<<grid, SY_THREADS, smem, st>>>(K, dvar, craw, which, MP, R, nc, part, clamp_count,
                                            which == 0 ? dmu : nullptr, which == 0 ? part_alpha : nullptr));
