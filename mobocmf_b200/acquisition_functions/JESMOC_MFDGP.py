@@ -45,11 +45,14 @@ class JESMOC_MFDGP():
         self.eval_highest_fidelity = eval_highest_fidelity
         self.blackbox_mfdgp_fitter_uncond = model.copy_uncond()
         if model_cond is None:
-            # Pareto-set sampling (RFF + MOOP) is outside the hot path; the fitter must already
-            # hold ``pareto_set`` / ``pareto_front`` (set them, or pass ``model_cond``).
+            # acquisition_functions/JESMOC_MFDGP.py:73-77: one Pareto-set sample (RFF function samples + MOOP, on the
+            # GPU), then the conditioned training.  A Pareto set already stored on the fitter (tests, replays of a
+            # given sample) is kept instead of drawing a new one.
             if getattr(model, "pareto_set", None) is None:
-                raise RuntimeError("provide model_cond or set model.pareto_set / model.pareto_front first")
-            self.pareto_set, self.pareto_front = model.pareto_set, model.pareto_front
+                self.pareto_set, self.pareto_front, self.samples_objs, self.samples_cons = \
+                    model.sample_and_store_pareto_solution()
+            else:
+                self.pareto_set, self.pareto_front = model.pareto_set, model.pareto_front
             model.train_conditioned_mfdgps()
             self.blackbox_mfdgp_fitter_cond = model
         else:

@@ -41,11 +41,10 @@ def test_forrester_fit_condition_acquire(use_cuda_graph, concurrent):
         # the three models trained on their own streams: every one of them moved and stayed finite
         for hh in list(fitter.mfdgp_handlers_objs.values()) + list(fitter.mfdgp_handlers_cons.values()):
             assert all(bool(torch.isfinite(p).all()) for p in hh.mfdgp.parameters())
-        # Pareto set by RFF function samples + MOOP (fitter.py:181-225) on the GPU
+        # the Pareto set is drawn by JESMOC_MFDGP itself below, like in the reference
+        # (acquisition_functions/JESMOC_MFDGP.py:73-77): RFF function samples + MOOP on the GPU
         import numpy as np
         np.random.seed(4)
-        pset, pfront, _, _ = fitter.sample_and_store_pareto_solution()
-        assert pset.shape[1] == 1 and pfront.shape == (pset.shape[0], 2) and 1 <= pset.shape[0] <= 6
     else:
         g = torch.Generator().manual_seed(1)
         fitter.pareto_set = torch.rand(6, 1, generator=g, dtype=torch.float64)
@@ -53,6 +52,9 @@ def test_forrester_fit_condition_acquire(use_cuda_graph, concurrent):
     fitter.num_epochs_2 = 15
     bounds = torch.tensor([[0.0], [1.0]], dtype=torch.float64, device=DEV)
     acq = JESMOC_MFDGP(model=fitter, num_fidelities=L, standard_bounds=bounds)
+    if concurrent:
+        pset, pfront = acq.pareto_set, acq.pareto_front
+        assert pset.shape[1] == 1 and pfront.shape == (pset.shape[0], 2) and 1 <= pset.shape[0] <= 6
     for f in range(L):
         acq.add_blackbox(f, "obj1", cost_evaluation=1.0 + f)
         acq.add_blackbox(f, "obj2", cost_evaluation=1.0 + f)
