@@ -209,6 +209,17 @@ class MFDGPHiddenLayer(nn.Module):
         state["_dev_cache"] = {}
         return state
 
+    def print_lengthscales_and_outputscale(self, custom_print):
+        """layers/mfdgp_hidden_layer.py:190-224: the constrained hyper-parameters, named as in the reference."""
+        th = self.theta().detach().cpu().numpy()
+        if self.num_layer == 0:
+            custom_print({"l0_lengthscale:": th[1:], "l0_outputscale:": float(th[0])})
+            return
+        d = self.x_dims
+        custom_print({"l1_lengthscale_x1:": th[5:5 + d], "l1_lengthscale_f:": th[3:4], "l1_lengthscale_x2:": th[5 + d:],
+                      "l1_alpha_x1:": float(th[0]), "l1_alpha_f:": float(th[2]), "l1_alpha_x1f:": float(th[0] * th[2]),
+                      "l1_alpha_x2:": float(th[4]), "l1_nu_lin:": float(th[1])})
+
     def train_mode(self):
         self._eval_mode = False
 

@@ -248,6 +248,10 @@ class MFDGP(nn.Module):
     # ---- fused acquisition chain (mobo_acq_moments): no autograd graph, one enqueue per model ----
     ACQ_CHUNK = 1 << 18      # candidates per enqueue (bounds the n * S scratch)
 
+    def clip_inducing_values(self, x_0, x_1, y_1):
+        """y_1 at the point of x_1 nearest to each row of x_0 (models/mfdgp.py:125-135)."""
+        return y_1[torch.argmin(torch.cdist(x_0, x_1), dim=1)]
+
     # ---- function samples of every layer (models/mfdgp.py:264-288) ----
     def sample_function_from_each_layer(self, nFeatures=500):
         result, last = [], None

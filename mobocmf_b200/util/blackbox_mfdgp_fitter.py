@@ -516,6 +516,13 @@ class BlackBoxMFDGPFitter():
         for h in list(self.mfdgp_handlers_objs.values()) + list(self.mfdgp_handlers_cons.values()):
             h.mfdgp.train()
 
+    def mfdgps_to_eval_mode(self):
+        """fitter.py:363-368, as written there: the objectives' models to eval(), the constraints' to train()."""
+        for h in self.mfdgp_handlers_objs.values():
+            h.mfdgp.eval()
+        for h in self.mfdgp_handlers_cons.values():
+            h.mfdgp.train()
+
     def copy_uncond(self):
         if self.models_uncond_trained is False:
             warnings.warn("(Warning) The mfdgp models have not been trained yet.")

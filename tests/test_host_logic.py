@@ -114,3 +114,21 @@ def test_operator_buffer_layout_mirror_matches_library():
         lay = ops_layout(M)
         assert lay["MP"] == lib.mobo_padded_m(M) == padded_m(M)
         assert lay["size"] == lib.mobo_ops_doubles(M)
+
+
+def test_small_host_helpers(tmp_path):
+    """Host helpers mirrored from mobocmf/util/util.py and models/mfdgp.py:125-135."""
+    import numpy as np
+    from mobocmf_b200.models.mfdgp import MFDGP
+    from mobocmf_b200.util import util
+    a, b, mean, std = util.preprocess_outputs(np.array([[1.0], [2.0]]), np.array([[3.0]]))
+    assert a.dtype == torch.float64 and float(a[1]) == 2.0 and float(b[0]) == 3.0 and (mean, std) == (0.0, 1.0)
+    lo, hi, mean, std = util.preprocess_outputs_two_fidelities(np.array([[1.0]]), np.array([[4.0]]))
+    assert float(lo) == 1.0 and float(hi) == 4.0
+    util.save_pickle(str(tmp_path / "sub"), "x.pkl", {"k": torch.arange(3)})
+    assert torch.equal(util.read_pickle(str(tmp_path / "sub"), "x.pkl")["k"], torch.arange(3))
+    x0 = torch.tensor([[0.0], [0.9], [0.52]], dtype=torch.float64)
+    x1 = torch.tensor([[0.1], [0.5], [1.0]], dtype=torch.float64)
+    y1 = torch.tensor([[10.0], [20.0], [30.0]], dtype=torch.float64)
+    assert torch.equal(MFDGP.clip_inducing_values(None, x0, x1, y1), torch.tensor([[10.0], [30.0], [20.0]],
+                                                                                dtype=torch.float64))
