@@ -484,9 +484,17 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
     __syncthreads();   // every warp is done reading K
     if (active) store_acc_to_tile(acc, Ks, ldb, sA, sB, half, lane);
     __syncthreads();
-    if (a.Tsave) {     // whitened rows t = W k, row-major [R][MP], for the backward (SYRK statistics and dt)
-      for (int r = warp; r < nvalid; r += ROW_WARPS)
-        for (int j = lane; j < MP; j += 32) a.Tsave[(size_t)(row0 + r) * MP + j] = Ks[(size_t)r * ldb + j];
+    // whitened rows t = W k, row-major [R][MP], for the backward (SYRK statistics and dt): one bulk (TMA engine)
+    // shared -> global copy per row, issued by warp 0, instead of 32 shared loads + 32 global stores per thread; the
+    // copies read the tile while the second product does, and are waited for before the tile is rebuilt
+    if (a.Tsave && warp == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes of t -> async-proxy reads
+      if (lane < nvalid)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                         a.Tsave + (size_t)(row0 + lane) * MP),
+                     "r"((unsigned)__cvta_generic_to_shared(Ks + (size_t)lane * ldb)),
+                     "r"((unsigned)(MP * sizeof(double))) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     // ---- u = H^T t ----
     if (active) {
@@ -522,6 +530,7 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
       if (a.craw) a.craw[row0 + tid] = c;
       if (a.training && c < 0.0 && a.clamp_count) atomicAdd(a.clamp_count, 1u);
     }
+    if (a.Tsave && warp == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();
   }
 }
