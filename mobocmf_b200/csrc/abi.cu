@@ -478,10 +478,8 @@ int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
     // slower); the fold of its partials and the latency-bound operator-chain backward of this layer go to the side
     // stream
     double* gl = ws + y.gops[l];
-    MOBO_TRY(launch_syrk_main(ws + y.Ts[l], ws + y.dvar[l], ws + y.craw[l], 0, MP, R, ws + y.stats0[l], clamp + l,
-                              ws + y.dmu[l], ws + y.stats_alpha[l], st));
-    MOBO_TRY(launch_syrk_main(ws + y.Ts[l], ws + y.dvar[l], ws + y.craw[l], 1, MP, R, ws + y.stats1[l], clamp + l,
-                              nullptr, nullptr, st));
+    MOBO_TRY(launch_syrk_both(ws + y.Ts[l], ws + y.dvar[l], ws + y.craw[l], MP, R, ws + y.stats0[l], ws + y.stats1[l],
+                              clamp + l, ws + y.dmu[l], ws + y.stats_alpha[l], st));
     if (fork && (cudaEventRecord(sc.fork[l], st) != cudaSuccess || cudaStreamWaitEvent(ss, sc.fork[l], 0) != cudaSuccess))
       return -1;
     MOBO_TRY(launch_syrk_reduce(0, MP, R, ws + y.stats0[l], gl + ops_block(MP, OPS_W), clamp + l, ws + y.stats_alpha[l],

@@ -1031,9 +1031,15 @@ __host__ __device__ inline size_t syrk_stage_doubles(int MP) { return (size_t)SY
 __host__ __device__ inline int syrk_nblocks(int MP) { const int nb = MP / 32; return nb * (nb + 1) / 2; }
 
 __global__ void __launch_bounds__(SY_THREADS, 1)
-syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const double* __restrict__ craw, int which,
-            int MP, long long R, int nchunk, double* __restrict__ part, const unsigned int* __restrict__ clamp_count,
-            const double* __restrict__ dmu, double* __restrict__ part_alpha) {
+syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const double* __restrict__ craw, int which_in,
+            int MP, long long R, int nchunk, double* __restrict__ part_in, const unsigned int* __restrict__ clamp_count,
+            const double* __restrict__ dmu_in, double* __restrict__ part_alpha_in, double* __restrict__ part_clamped) {
+  // which_in == 2: both weight sets in one launch, blockIdx.z = which (the clamped-rows set, which is almost always
+  // skipped, then costs no launch of its own)
+  const int which = which_in == 2 ? (int)blockIdx.z : which_in;
+  double* __restrict__ part = (which_in == 2 && which == 1) ? part_clamped : part_in;
+  const double* __restrict__ dmu = which == 0 ? dmu_in : nullptr;
+  double* __restrict__ part_alpha = which == 0 ? part_alpha_in : nullptr;
   if (which == 1 && (clamp_count == nullptr || *clamp_count == 0u)) return;
   extern __shared__ __align__(16) double sy_sh[];
   __shared__ unsigned long long full[SY_STAGES];     // mbarriers: stage s % SY_STAGES has landed
@@ -1294,7 +1300,23 @@ int launch_syrk_main(const double* K, const double* dvar, const double* craw, in
                          (int)(SY_STAGES * syrk_stage_doubles(MAX_MP) * sizeof(double)));
   dim3 grid(syrk_ngroups(MP), nc);
   MOBO_LAUNCH("syrk_kernel", st, syrk_kernel<<<grid, SY_THREADS, smem, st>>>(K, dvar, craw, which, MP, R, nc, part, clamp_count,
-                                           which == 0 ? dmu : nullptr, which == 0 ? part_alpha : nullptr));
+                                           which == 0 ? dmu : nullptr, which == 0 ? part_alpha : nullptr, nullptr));
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// both weight sets (all rows -> part, clamped rows only -> part_clamped) in ONE launch
+int launch_syrk_both(const double* K, const double* dvar, const double* craw, int MP, long long R, double* part,
+                     double* part_clamped, const unsigned int* clamp_count, const double* dmu, double* part_alpha,
+                     cudaStream_t st) {
+  const int nc = syrk_nchunk(MP, R);
+  const size_t smem = SY_STAGES * syrk_stage_doubles(MP) * sizeof(double);
+  static bool attr_done[kMaxDevices] = {false};
+  if (first_on_device(attr_done))
+    cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(SY_STAGES * syrk_stage_doubles(MAX_MP) * sizeof(double)));
+  dim3 grid(syrk_ngroups(MP), nc, 2);
+  MOBO_LAUNCH("syrk_kernel", st, syrk_kernel<<<grid, SY_THREADS, smem, st>>>(K, dvar, craw, 2, MP, R, nc, part, clamp_count, dmu,
+                                           part_alpha, part_clamped));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
