@@ -93,16 +93,27 @@ int mobo_kzz(int kind, int d, int M, const double* Zx, const double* zf, const d
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+static int model_precompute(int nl, const int* kinds, int d, int M, const double* const* Zx, const double* const* zf,
+                            const double* const* theta, const double* const* m, const double* const* Lq,
+                            double jitter, double* const* ops, void* stream, bool reset_flags);
+
 int mobo_model_precompute(int nl, const int* kinds, int d, int M, const double* const* Zx, const double* const* zf,
                           const double* const* theta, const double* const* m, const double* const* Lq,
                           double jitter, double* const* ops, void* stream) {
+  return model_precompute(nl, kinds, d, M, Zx, zf, theta, m, Lq, jitter, ops, stream, true);
+}
+
+// reset_flags = false: the caller has already zeroed the flags region of every operator buffer on this stream
+static int model_precompute(int nl, const int* kinds, int d, int M, const double* const* Zx, const double* const* zf,
+                            const double* const* theta, const double* const* m, const double* const* Lq,
+                            double jitter, double* const* ops, void* stream, bool reset_flags) {
   cudaStream_t st = (cudaStream_t)stream;
   LayerBatch b;
   MOBO_TRY(fill_batch(b, nl, kinds, d, M, Zx, zf, theta, m, Lq, ops));
   const int MP = b.MP;
   // one cooperative launch: a CTA per 32 x 32 block of the lower triangle of every layer (opchain.cu)
   const int nb = MP / 32, nblk = nb * (nb + 1) / 2;
-  MOBO_LAUNCH("opchain_reset_kernel", st, opchain_reset_kernel<<<nl, 128, 0, st>>>(b));
+  if (reset_flags) MOBO_LAUNCH("opchain_reset_kernel", st, opchain_reset_kernel<<<nl, 128, 0, st>>>(b));
   void* args[] = {(void*)&b, (void*)&jitter};
   prof_begin("opchain_kernel", st);
   const cudaError_t e = cudaLaunchCooperativeKernel((const void*)opchain_kernel, dim3(nl * nblk), dim3(OC_THREADS), args,
@@ -444,11 +455,12 @@ int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
       a.theta[l] = ok ? ws + y.theta[l] : nullptr;
       a.gops_scal[l] = ok ? ws + y.gops[l] + ops_scal(MP) : nullptr;
       a.ops_scal[l] = ok ? ws + y.ops[l] + ops_scal(MP) : nullptr;
+      a.oc_flags[l] = ok ? reinterpret_cast<int*>(ws + y.ops[l] + ops_flags(MP)) : nullptr;
     }
     MOBO_LAUNCH("step_prep_kernel", st, step_prep_kernel<<<L, 96, 0, st>>>(a));
   }
   // 2. operator chain of every layer
-  MOBO_TRY(mobo_model_precompute(L, kinds, d, M, Zx, zf, theta, m, Lq, D->jitter, ops, stream));
+  MOBO_TRY(model_precompute(L, kinds, d, M, Zx, zf, theta, m, Lq, D->jitter, ops, stream, false));
   // 3. forward row passes, low -> high fidelity
   for (int l = 0; l < L; ++l) {
     const long long R = y.R[l];

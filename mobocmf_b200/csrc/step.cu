@@ -35,6 +35,7 @@ struct PrepArgs {
   double* ops_scal[ST_MAX_LAYERS];    // scal block of each operator buffer (holds finalize_kernel's arrival counter)
   unsigned int* clamp_count;          // [L]
   double dkl;                         // d loss / d KL = B / N
+  int* oc_flags[ST_MAX_LAYERS];       // block-to-block flags of the operator-chain kernel (256 ints), zeroed here
 };
 
 __global__ void step_prep_kernel(const __grid_constant__ PrepArgs a) {
@@ -47,6 +48,8 @@ __global__ void step_prep_kernel(const __grid_constant__ PrepArgs a) {
     a.gops_scal[l][tid - 64] = (tid - 64 == SC_KL) ? a.dkl : 0.0;
     a.ops_scal[l][tid - 64] = 0.0;    // the workspace is caller memory: never assume it is zeroed
   }
+  // what opchain_reset_kernel does for the stand-alone entry point: one launch less on the step's critical path
+  for (int i = tid; i < 256; i += blockDim.x) a.oc_flags[l][i] = 0;
 }
 
 // ---- expected log-likelihood of one layer's rows + the seed of its backward -------------------------
