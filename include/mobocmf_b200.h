@@ -15,7 +15,8 @@
  *   MP = M rounded up to a multiple of 32.  An "operator buffer" is mobo_ops_doubles(M) doubles laid out as
  *   [L | W | WT | H | HT | P | LQ] (seven MP x MP row-major blocks), [WF | HTF | HF | WTF] (W, HT, H, WT again in the
  *   DMMA A-fragment order the row kernels stream them in), beta[MP], alpha[MP], scal[16], rowstat[4 MP], flags[128]
- *   (scal[0] = KL, scal[5] = Cholesky status: 0 ok, 1 not positive definite).
+ *   (scal[0] = KL, scal[5] = Cholesky status: 0 ok, 1 not positive definite after the three psd_safe_cholesky
+ *   retries with 1e-8, 1e-7, 1e-6 more on the diagonal, scal[7] = retries used).
  *   The GRADIENT of an operator buffer uses the same layout and, by convention, carries only
  *   block W: A2 = sum_r dvar_r t_r t_r^T (t = W k, whitened), block H: the same sum over clamped rows,
  *   alpha: b = sum_r dmu_r t_r,
@@ -28,7 +29,7 @@
 extern "C" {
 #endif
 
-/* library / build identification: returns 100 for sm_100a */
+/* library / build identification: 101 (sm_100a; 100 + ABI revision) */
 int mobo_abi_version(void);
 
 /* Launch accounting: number of kernels this library has launched in this process; optional per-launch CUDA-event
@@ -140,8 +141,12 @@ typedef struct mobo_step_desc {
   const double* y;                             /* B                                                              */
   const double* fid;                           /* B, fidelity index stored as double (as the reference does)     */
   mobo_layer_desc layer[MOBO_MAX_LAYERS];
-  double* out;                                 /* [0] loss = -ELBO, [1] KL*B/N, [2] data term, [3] status: 0 ok,
-                                                  l+1 = Cholesky of layer l failed (NotPSDError upstream)        */
+  double* out;                                 /* 8 doubles: [0] loss = -ELBO, [1] KL*B/N, [2] data term, [3] status:
+                                                  0 ok, l+1 = Cholesky of layer l failed after psd_safe_cholesky's
+                                                  three jitter retries (NotPSDError upstream); [4] first non-zero
+                                                  status since the caller last zeroed it (sticky); [5] sticky "loss not
+                                                  finite" (NanError upstream); [6] 1 when THIS step failed either way
+                                                  (pass &out[6] to mobo_adam as skip_flag); [7] retries used (0..3)  */
   double* workspace;                           /* mobo_elbo_step_workspace_doubles(...) doubles                  */
   int accumulate;                              /* 0: gradients are overwritten, 1: added to                      */
 } mobo_step_desc;
@@ -155,11 +160,12 @@ int mobo_elbo_step(const mobo_step_desc* desc, void* stream);
 /* torch.optim.Adam update (mobocmf/util/blackbox_mfdgp_fitter.py:126,132,259; defaults betas (0.9, 0.999),
  * eps 1e-8, no weight decay) of nt <= 64 tensors in one launch.  step = 1-based step count after increment, or, for
  * CUDA-graph replays, step_dev != NULL: a device-resident count (advance it with mobo_adam_tick before each update;
- * `step` is then ignored). */
+ * `step` is then ignored).  skip_flag (optional, device): when *skip_flag != 0 nothing is updated - the step that
+ * produced the gradients failed (upstream raises NotPSDError / NanError before optimizer.step() is reached). */
 typedef struct mobo_adam_tensor { double* p; const double* g; double* exp_avg; double* exp_avg_sq; long long n; } mobo_adam_tensor;
 int mobo_adam(int nt, const mobo_adam_tensor* tensors, double lr, double beta1, double beta2, double eps,
-              long long step, long long* step_dev, void* stream);
-int mobo_adam_tick(long long* step_dev, void* stream);
+              long long step, long long* step_dev, const double* skip_flag, void* stream);
+int mobo_adam_tick(long long* step_dev, const double* skip_flag, void* stream);
 
 /* Acquisition chain of ONE MFDGP in eval mode: MFDGP.predict_for_acquisition (mobocmf/models/mfdgp.py:237-262) for n
  * candidates x S fixed normals per layer, up to layer `fidelity`, from precomputed operator buffers (the parameters

@@ -91,10 +91,16 @@ class JESMOC_MFDGP():
         (acquisition_functions/JESMOC_MFDGP.py:127-133, quirk Q8); pass ``float32_accumulator=False`` for fp64."""
         acq = torch.zeros(size=(X.shape[0],), device=X.device,
                           dtype=torch.float32 if float32_accumulator else torch.float64)
+
+        def add(acq, term):
+            # `acq(float32) += term(float64)` in place: torch computes the sum in the promoted type (fp64) and rounds
+            # the RESULT to the accumulator's type once - not round(term) + acq in fp32
+            return (acq.double() + term).to(acq.dtype)
+
         for name_obj, obj in self.objectives[fidelity].items():
-            acq = acq + obj(X.double()).to(acq.dtype)
+            acq = add(acq, obj(X.double()))
         for name_con, con in self.constraints[fidelity].items():
-            acq = acq + con(X.double()).to(acq.dtype)
+            acq = add(acq, con(X.double()))
         return acq
 
     def _optimize(self, fidelity):

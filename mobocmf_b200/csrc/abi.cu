@@ -15,7 +15,7 @@ static inline int padded(int M) { return ((M + 31) / 32) * 32; }
 
 extern "C" {
 
-int mobo_abi_version(void) { return 100; }
+int mobo_abi_version(void) { return 101; }
 
 long long mobo_launch_count(void) { return prof_state().launches; }
 
@@ -550,11 +550,11 @@ int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
 }
 
 int mobo_adam(int nt, const mobo_adam_tensor* tensors, double lr, double beta1, double beta2, double eps,
-              long long step, long long* step_dev, void* stream) {
+              long long step, long long* step_dev, const double* skip_flag, void* stream) {
   if (nt < 1 || nt > ADAM_MAX_TENSORS || (step < 1 && !step_dev)) return -2;
   cudaStream_t st = (cudaStream_t)stream;
   AdamArgs a;
-  a.nt = nt; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.step_dev = step_dev;
+  a.nt = nt; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.step_dev = step_dev; a.skip = skip_flag;
   a.bc1 = step_dev ? 1.0 : 1.0 - pow(beta1, (double)step);
   a.bc2_sqrt = step_dev ? 1.0 : sqrt(1.0 - pow(beta2, (double)step));
   long long mx = 1;
@@ -571,9 +571,9 @@ int mobo_adam(int nt, const mobo_adam_tensor* tensors, double lr, double beta1, 
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-int mobo_adam_tick(long long* step_dev, void* stream) {
+int mobo_adam_tick(long long* step_dev, const double* skip_flag, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  MOBO_LAUNCH("adam_tick_kernel", st, adam_tick_kernel<<<1, 1, 0, st>>>(step_dev));
+  MOBO_LAUNCH("adam_tick_kernel", st, adam_tick_kernel<<<1, 1, 0, st>>>(step_dev, skip_flag));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -59,8 +59,9 @@ __host__ __device__ inline size_t frag_offset(int MP, int i, int k) {
   return ((size_t)(i >> 4) * (MP >> 2) + (k >> 2)) * 64 + 2 * (4 * (i & 7) + (k & 3)) + ((i >> 3) & 1);
 }
 // scal[SC_CLAMP] is meaningful in the GRADIENT buffer: number of clamped rows behind block OPS_H (0 -> Ac == 0)
+// scal[SC_RETRIES]: number of psd_safe_cholesky retries the operator chain needed (0 .. 3); SC_STATUS = 1: all failed
 enum OpsScal { SC_KL = 0, SC_LOGDET_P = 1, SC_LOGDET_Q = 2, SC_BETA2 = 3, SC_H2 = 4, SC_STATUS = 5, SC_CLAMP = 6,
-               SC_COUNTER = 8 };
+               SC_RETRIES = 7, SC_COUNTER = 8 };
 __host__ __device__ inline size_t ops_block(int MP, int b) { return (size_t)b * MP * MP; }
 __host__ __device__ inline size_t ops_beta(int MP) { return (size_t)OPS_NBLOCKS * MP * MP; }
 __host__ __device__ inline size_t ops_alpha(int MP) { return (size_t)OPS_NBLOCKS * MP * MP + MP; }

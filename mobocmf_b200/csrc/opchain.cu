@@ -21,8 +21,9 @@ namespace mobo {
 
 constexpr int OC_THREADS = 128, OC_LD = 36, OC_MAXBLK = 64;
 
-// flags region of an operator buffer, as ints: [0, 64) L-block done, [64, 128) W-block done, [128] arrival counter,
-// [129] failure (non-positive pivot)
+// flags region of an operator buffer, as ints: [0, 64) L-block done, [64, 128) W-block done (value = attempt that
+// produced the block, 1-based), [128] arrival counter, [129 + a] attempt a hit a non-positive pivot (a = 0 .. 3)
+constexpr int OC_FAIL = 129, OC_MAX_RETRIES = 3;
 __device__ __forceinline__ int* oc_flags(double* ops, int MP) { return reinterpret_cast<int*>(ops + ops_flags(MP)); }
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -33,20 +34,21 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// every thread of the CTA may read the producer's data after this returns
-__device__ __forceinline__ void oc_wait(const int* flag) {
+// Flags carry the number of the factorisation attempt that produced the block (1-based, see the retry loop of
+// opchain_kernel): every thread of the CTA may read the producer's data of attempt `want` after this returns
+__device__ __forceinline__ void oc_wait(const int* flag, int want) {
   if (threadIdx.x == 0) {
-    while (ld_acquire(flag) == 0) __nanosleep(40);
+    while (ld_acquire(flag) < want) __nanosleep(40);
   }
   __syncthreads();
 }
 // call after the CTA's global writes; makes them visible before the flag(s)
-__device__ __forceinline__ void oc_signal(int* flag, int* flag2 = nullptr) {
+__device__ __forceinline__ void oc_signal(int want, int* flag, int* flag2 = nullptr) {
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    st_release(flag, 1);
-    if (flag2) st_release(flag2, 1);
+    st_release(flag, want);
+    if (flag2) st_release(flag2, want);
   }
 }
 
@@ -133,10 +135,23 @@ __global__ void opchain_reset_kernel(LayerBatch b) {
   for (int i = threadIdx.x; i < 256; i += blockDim.x) fl[i] = 0;
 }
 
+// attempt > 0: upstream psd_safe_cholesky's retries (linear_operator, reached through UnwhitenedVariationalStrategy):
+// Aprime.diagonal().add_(1e-8 * 10^i - previous) for i = 0 .. attempt - 1, the same sequence of fp64 additions
 __device__ inline double oc_kernel_entry(const KernParams& kp, int kind, int d, const double* __restrict__ Zx,
-                                         const double* __restrict__ zf, int M, int i, int j, double jitter) {
+                                         const double* __restrict__ zf, int M, int i, int j, double jitter,
+                                         int attempt) {
   if (i >= M || j >= M) return i == j ? 1.0 : 0.0;
-  if (i == j) return kern_diag(kp, kind == 1 ? zf[i] : 0.0) + jitter;
+  if (i == j) {
+    double v = kern_diag(kp, kind == 1 ? zf[i] : 0.0) + jitter;
+    double prev = 0.0, p10 = 1.0;
+    for (int a = 0; a < attempt; ++a) {
+      const double jn = 1e-8 * p10;
+      v += jn - prev;
+      prev = jn;
+      p10 *= 10.0;
+    }
+    return v;
+  }
   double D1 = 0.0, D2 = 0.0;
   for (int c = 0; c < d; ++c) {
     const double df = Zx[(size_t)i * d + c] - Zx[(size_t)j * d + c];
@@ -152,7 +167,8 @@ __device__ inline double oc_kernel_entry(const KernParams& kp, int kind, int d, 
 __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, double jitter) {
   __shared__ __align__(16) double Abuf[32 * OC_LD], Bbuf[32 * OC_LD], Cbuf[32 * OC_LD], Dbuf[32 * OC_LD];
   __shared__ KernParams kp;
-  __shared__ int fail_flag;
+  __shared__ bool retry;
+  __shared__ double part[4][4];     // [warp][h2, beta2, logdetP, logdetQ]
   __shared__ double rdiag[32];
   __shared__ bool last;
   const int MP = b.MP, M = b.M, d = b.d;
@@ -180,13 +196,23 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
   const double* zf = b.zf[layer];
   const double* Lq = b.Lq[layer];
   const double* mvec = b.m[layer];
+  double* rowstat = ops + ops_rowstat(MP);     // [nblk][4] per-CTA partials
 
   OC_TICK(0);
-  if (tid == 0) { load_kern_params(kp, kind, d, b.theta[layer]); fail_flag = 0; }
+  if (tid == 0) load_kern_params(kp, kind, d, b.theta[layer]);
   __syncthreads();
 
-  // ---- own block of P = K(Z, Z) + jitter I (identity padded) ----
+  // Upstream factors P with psd_safe_cholesky: when a pivot is not positive the factorisation is retried with
+  // 1e-8, 1e-7, 1e-6 more on the diagonal.  Here every CTA runs the attempt to its end (a failed
+  // attempt only produces garbage that nobody keeps; the flags still advance, so nothing dead-locks), learns the
+  // outcome from the last diagonal block's flag + the attempt's failure flag, and all CTAs repeat together.  Flags
+  // hold the attempt number, so a block of attempt a is never taken for one of attempt a + 1; the success path pays
+  // one acquire load.
+  int attempt = 0;
   double acc[2][2][2];
+  for (;; ++attempt) {
+  const int want = attempt + 1;
+  // ---- own block of P = K(Z, Z) + jitter I (identity padded) ----
 #pragma unroll
   for (int x = 0; x < 2; ++x)
 #pragma unroll
@@ -194,7 +220,7 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int r = 16 * wr + 8 * x + g, c = 16 * wc + 8 * y + 2 * t + e;
-        acc[x][y][e] = oc_kernel_entry(kp, kind, d, Zx, zf, M, 32 * bi + r, 32 * bj + c, jitter);
+        acc[x][y][e] = oc_kernel_entry(kp, kind, d, Zx, zf, M, 32 * bi + r, 32 * bj + c, jitter, attempt);
       }
   oc_acc_to_smem(acc, Cbuf, wr, wc, g, t);
   __syncthreads();
@@ -204,8 +230,8 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
   OC_TICK(1);
   // ---- factorisation ----
   for (int k = 0; k < bj; ++k) {
-    oc_wait(Lflag(bi, k));
-    if (!diag) oc_wait(Lflag(bj, k));
+    oc_wait(Lflag(bi, k), want);
+    if (!diag) oc_wait(Lflag(bj, k), want);
     oc_load(Abuf, blk(Lg, bi, k), MP);
     if (!diag) oc_load(Bbuf, blk(Lg, bj, k), MP);
     __syncthreads();
@@ -222,7 +248,7 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
       for (int c = 0; c < 32; ++c) row[c] = Cbuf[lane * OC_LD + c];
       int fail = 0;
       chol32_inwarp(row, rinv, lane, fail);
-      if (fail) fail_flag = 1;
+      if (fail && lane == 0) atomicExch(flags + OC_FAIL + attempt, 1);   // ordered before the block's flags below
 #pragma unroll
       for (int c = 0; c < 32; ++c) Abuf[lane * OC_LD + c] = c <= lane ? row[c] : 0.0;   // L_jj
       rdiag[lane] = rinv;
@@ -246,11 +272,11 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
     oc_store(blk(Lg, bi, bi), MP, Abuf, false);
     oc_store(blk(Wg, bi, bi), MP, Dbuf, false);
     oc_store(blk(WTg, bi, bi), MP, Dbuf, true);
-    oc_signal(Lflag(bi, bi), Wflag(bi, bi));
+    oc_signal(want, Lflag(bi, bi), Wflag(bi, bi));
     OC_TICK(4);
   } else {
     oc_acc_to_smem(acc, Abuf, wr, wc, g, t);
-    oc_wait(Lflag(bj, bj));
+    oc_wait(Lflag(bj, bj), want);
     oc_load(Bbuf, blk(Wg, bj, bj), MP);
     __syncthreads();
     oc_zero_acc(acc);
@@ -260,13 +286,13 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
     __syncthreads();
     oc_store(blk(Lg, bi, bj), MP, Cbuf, false);
     oc_zero_block(blk(Lg, bj, bi), MP);
-    oc_signal(Lflag(bi, bj));
+    oc_signal(want, Lflag(bi, bj));
     OC_TICK(3);
     // ---- inverse: W_ij = -D_i sum_{k=j}^{i-1} L_ik W_kj ----
     oc_zero_acc(acc);
     for (int k = bj; k < bi; ++k) {
-      if (k != bj) oc_wait(Lflag(bi, k));
-      oc_wait(Wflag(k, bj));
+      if (k != bj) oc_wait(Lflag(bi, k), want);
+      oc_wait(Wflag(k, bj), want);
       if (k != bj) oc_load(Abuf, blk(Lg, bi, k), MP);
       else for (int idx = tid; idx < 32 * OC_LD; idx += OC_THREADS) Abuf[idx] = Cbuf[idx];   // own L_ij
       oc_load(Bbuf, blk(Wg, k, bj), MP);
@@ -275,7 +301,7 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
       __syncthreads();
     }
     oc_acc_to_smem(acc, Bbuf, wr, wc, g, t);                                            // S
-    oc_wait(Lflag(bi, bi));
+    oc_wait(Lflag(bi, bi), want);
     oc_load(Abuf, blk(Wg, bi, bi), MP);                                                 // D_i
     __syncthreads();
     oc_zero_acc(acc);
@@ -287,7 +313,7 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
     oc_store(blk(WTg, bj, bi), MP, Dbuf, true);
     oc_zero_block(blk(Wg, bj, bi), MP);
     oc_zero_block(blk(WTg, bi, bj), MP);
-    oc_signal(Wflag(bi, bj));
+    oc_signal(want, Wflag(bi, bj));
     OC_TICK(4);
   }
   // here Dbuf = own W_ij (diag: D_j)
@@ -297,7 +323,7 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
   for (int k = bj; k <= bi; ++k) {
     const double* Asrc = Dbuf;
     if (k != bj) {
-      if (k == bi) oc_wait(Lflag(bi, bi)); else oc_wait(Wflag(bi, k));
+      if (k == bi) oc_wait(Lflag(bi, bi), want); else oc_wait(Wflag(bi, k), want);
       oc_load(Abuf, blk(Wg, bi, k), MP);
       Asrc = Abuf;
     }
@@ -339,7 +365,6 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
 #pragma unroll
       for (int e = 0; e < 2; ++e) h2 = fma(acc[x][y][e], acc[x][y][e], h2);
   h2 = warp_sum(h2);
-  __shared__ double part[4][4];     // [warp][h2, beta2, logdetP, logdetQ]
   if (lane == 0) { part[warp][0] = h2; part[warp][1] = 0.0; part[warp][2] = 0.0; part[warp][3] = 0.0; }
   if (diag) {
     // beta_i = sum_{k <= i} W_ik m_k : 4 threads per row, each over a quarter of every 32-block
@@ -348,7 +373,7 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
     for (int k = 0; k <= bi; ++k) {
       const double* Ws = Dbuf;
       if (k != bi) {
-        oc_wait(Wflag(bi, k));
+        oc_wait(Wflag(bi, k), want);
         oc_load(Abuf, blk(Wg, bi, k), MP);
         __syncthreads();
         Ws = Abuf;
@@ -377,9 +402,13 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
     if (lane == 0) { part[warp][1] = b2; part[warp][2] = ldp; part[warp][3] = ldq; }
   }
   __syncthreads();
-  double* rowstat = ops + ops_rowstat(MP);     // [nblk][4] per-CTA partials
   if (tid < 4) rowstat[4 * q + tid] = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
-  if (tid == 0 && fail_flag) atomicExch(flags + 129, 1);
+  // ---- did this attempt factor P?  The last diagonal block is factored after every other one ----
+  oc_wait(Lflag(nb - 1, nb - 1), want);
+  if (tid == 0) retry = ld_acquire(flags + OC_FAIL + attempt) != 0 && attempt < OC_MAX_RETRIES;
+  __syncthreads();
+  if (!retry) break;
+  }  // attempts
   __threadfence();
   __syncthreads();
   OC_TICK(6);
@@ -398,7 +427,8 @@ __global__ void __launch_bounds__(OC_THREADS) opchain_kernel(LayerBatch b, doubl
       double* scal = ops + ops_scal(MP);
       scal[SC_H2] = v[0]; scal[SC_BETA2] = v[1]; scal[SC_LOGDET_P] = v[2]; scal[SC_LOGDET_Q] = v[3];
       scal[SC_KL] = 0.5 * (v[2] - v[3] + v[1] + v[0] - (double)M);
-      scal[SC_STATUS] = ld_acquire(flags + 129) ? 1.0 : 0.0;
+      scal[SC_STATUS] = ld_acquire(flags + OC_FAIL + attempt) ? 1.0 : 0.0;
+      scal[SC_RETRIES] = (double)attempt;
     }
   }
 }

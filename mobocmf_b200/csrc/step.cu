@@ -136,7 +136,8 @@ struct FinishArgs {
   const double* ell_part[ST_MAX_LAYERS];
   int ell_blocks[ST_MAX_LAYERS];
   const double* ops_scal[ST_MAX_LAYERS];
-  double* out;                           // [0] loss, [1] KL * B / N, [2] data term, [3] status
+  double* out;                           // [0] loss, [1] KL * B / N, [2] data term, [3] status, [4] sticky status,
+                                         // [5] sticky "loss not finite", [6] this step is bad (Adam skips), [7] retries
   int accumulate;
 };
 
@@ -153,16 +154,25 @@ __global__ void __launch_bounds__(256) step_finish_kernel(const __grid_constant_
   }
   __syncthreads();
   if (tid == 0) {
-    double data = 0.0, kl = 0.0, status = 0.0;
+    double data = 0.0, kl = 0.0, status = 0.0, retries = 0.0;
     for (int l = 0; l < a.L; ++l) {
       data += sdata[l];
       kl += a.ops_scal[l][SC_KL];
       if (a.ops_scal[l][SC_STATUS] != 0.0 && status == 0.0) status = (double)(l + 1);
+      retries = fmax(retries, a.ops_scal[l][SC_RETRIES]);
     }
-    a.out[0] = -(data - kl * a.kl_scale);
+    const double loss = -(data - kl * a.kl_scale);
+    a.out[0] = loss;
     a.out[1] = kl * a.kl_scale;
     a.out[2] = data;
     a.out[3] = status;
+    // the host reads these at its own pace (no per-step synchronisation): the first failure sticks, and the optimiser
+    // update of a bad step is skipped on the device (mobo_adam's skip flag)
+    const bool finite = isfinite(loss);
+    if (status != 0.0 && a.out[4] == 0.0) a.out[4] = status;
+    if (!finite && status == 0.0) a.out[5] = 1.0;
+    a.out[6] = (status != 0.0 || !finite) ? 1.0 : 0.0;
+    a.out[7] = retries;
   }
   for (int l = 0; l < a.L; ++l) {
     const int nth = theta_size(l == 0 ? 0 : 1, a.d);
@@ -203,11 +213,16 @@ struct AdamArgs {
   long long n[ADAM_MAX_TENSORS];
   double lr, beta1, beta2, eps, bc1, bc2_sqrt;
   const long long* step_dev;     // optional device-resident step count (CUDA-graph replays): overrides bc1 / bc2_sqrt
+  const double* skip;            // optional device flag: != 0 -> leave parameters and moments untouched
 };
 
-__global__ void adam_tick_kernel(long long* step_dev) { *step_dev += 1; }
+__global__ void adam_tick_kernel(long long* step_dev, const double* skip) {
+  if (skip && *skip != 0.0) return;
+  *step_dev += 1;
+}
 
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamArgs a) {
+  if (a.skip && *a.skip != 0.0) return;
   const int t = blockIdx.y;
   const long long n = a.n[t];
   double* __restrict__ p = a.p[t];

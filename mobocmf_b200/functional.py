@@ -32,6 +32,36 @@ def _c(t):
     return None if t is None else t.detach().contiguous()
 
 
+# ---- Cholesky status of the composable path -------------------------------------------------------------------
+# The operator-chain kernel retries a failed factorisation like upstream's psd_safe_cholesky (+1e-8, +1e-7, +1e-6) and
+# records a final failure in the operator buffer.  Reading it would cost a device synchronisation per layer and step,
+# so every precompute ADDS its status into one sticky device counter per GPU (an asynchronous 1-element add, also
+# capturable in a CUDA graph) and the callers that already synchronise - the fitter at its reporting boundaries, the
+# acquisition optimiser when it returns - call ``check_status()``.
+_STICKY = {}
+
+
+def _record_status(ops, M):
+    dev = ops.device.index
+    sticky = _STICKY.get(dev)
+    if sticky is None:
+        sticky = _STICKY[dev] = torch.zeros(1, dtype=torch.float64, device=ops.device)
+    i = ops_layout(M)["scal"] + SC_STATUS
+    sticky.add_(ops.detach()[i:i + 1])
+
+
+def check_status(device=None):
+    """Raises ``NotPSDError`` if any operator chain since the last call failed on this device (synchronises)."""
+    from .errors import NotPSDError
+    for dev, sticky in list(_STICKY.items()):
+        if device is not None and torch.device(device).index not in (None, dev):
+            continue
+        if float(sticky) != 0.0:
+            sticky.zero_()
+            raise NotPSDError("NotPSDError: K(Z, Z) + jitter I is not positive definite (after the 1e-8, 1e-7, 1e-6 "
+                              "jitter retries)")
+
+
 class _LayerOperators(torch.autograd.Function):
     @staticmethod
     def forward(ctx, theta, zf, m, Lq, Zx, kind, jitter):
@@ -42,6 +72,7 @@ class _LayerOperators(torch.autograd.Function):
         _lib.check(lib.mobo_layer_precompute(kind, d, M, _lib.ptr(Zx_), _lib.ptr(zf_), _lib.ptr(theta_),
                                              _lib.ptr(m_), _lib.ptr(Lq_), float(jitter), _lib.ptr(ops),
                                              _lib.stream_ptr()), "mobo_layer_precompute")
+        _record_status(ops, M)
         ctx.save_for_backward(theta_, zf_, m_, Lq_, Zx_, ops)
         ctx.kind = kind
         return ops

@@ -14,6 +14,7 @@ import ctypes
 import torch
 
 from . import _lib
+from .errors import NanError, NotPSDError
 from .util.distributed import FlatGrads
 
 MAX_LAYERS = 8
@@ -78,10 +79,13 @@ class FusedELBOStep(object):
         self.M = self.layers[0].num_inducing
         self.d = model.input_dims
         self.device = self.layers[0]._Zx().device
+        # [0] loss, [1] KL B/N, [2] data term, [3] status, [4] sticky status, [5] sticky non-finite loss,
+        # [6] "this step failed" (the Adam kernel's skip flag), [7] psd_safe_cholesky retries (include/mobocmf_b200.h)
         self.out = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self.skip_flag = self.out[6:7]
         self.flat = None
-        self._ws = None
-        self._ws_key = None
+        self._ws = {}             # (B, S) -> workspace; entries referenced by a captured CUDA graph are pinned
+        self._ws_pinned = set()
         self._desc = StepDesc()
         self._sig = None
 
@@ -110,6 +114,9 @@ class FusedELBOStep(object):
         return tuple(sig)
 
     def _ensure_grads(self):
+        for p in self.model.parameters():
+            if not p.requires_grad and p.grad is not None:
+                p.grad = None      # frozen since an earlier phase: torch's zero_grad would have dropped it too
         params = [p for p in self.model.parameters() if p.requires_grad]
         if self.flat is None or [id(p) for p in self.flat.params] != [id(p) for p in params]:
             self.flat = FlatGrads(params)
@@ -157,14 +164,26 @@ class FusedELBOStep(object):
             self._build_desc()
             self._sig = sig
 
-    def _workspace(self, B, S):
+    MAX_UNPINNED_WORKSPACES = 2
+
+    def _workspace(self, B, S, pin=False):
+        """Scratch of the step for a (B, S) shape.  A captured CUDA graph bakes the workspace's address in, so a
+        workspace that a graph references (``pin=True``) lives as long as this object; the others are kept for the
+        last few shapes only (full batch + ragged last batch of an epoch)."""
         key = (B, S)
-        if self._ws_key != key:
+        ws = self._ws.get(key)
+        if ws is None:
+            loose = [k for k in self._ws if k not in self._ws_pinned]
+            while len(loose) >= self.MAX_UNPINNED_WORKSPACES:
+                del self._ws[loose.pop(0)]
             n = self.lib.mobo_elbo_step_workspace_doubles(self.L, self.d, self.M, S, B)
-            self._ws = None
-            self._ws = torch.empty(n, dtype=torch.float64, device=self.device)
-            self._ws_key = key
-        return self._ws
+            ws = torch.empty(n, dtype=torch.float64, device=self.device)
+            self._ws[key] = ws
+        else:
+            self._ws[key] = self._ws.pop(key)      # most recently used last
+        if pin:
+            self._ws_pinned.add(key)
+        return ws
 
     def applies(self, x_batch):
         """False when the minibatch equals the inducing inputs row for row: upstream then short-cuts layer 0 to
@@ -181,7 +200,8 @@ class FusedELBOStep(object):
         return not bool(torch.equal(x_batch, Z))
 
     # ---- the step ---------------------------------------------------------------------------------------------
-    def __call__(self, x_batch, y_batch, fidelities, eps=None, num_samples=1, accumulate=False, check_shortcut=True):
+    def __call__(self, x_batch, y_batch, fidelities, eps=None, num_samples=1, accumulate=False, check_shortcut=True,
+                 pin_workspace=False):
         """Returns (loss = -ELBO, KL * B / N) as 0-d device tensors (views of one result buffer, overwritten by the
         next call) and writes the gradients.  ``eps``: optional list indexed by layer of the training normals
         (B*S values for layers >= 1; reference: float32 ``torch.normal`` of shape (1, B), quirk Q6)."""
@@ -211,7 +231,7 @@ class FusedELBOStep(object):
         D.layer[0].eps = None
         D.S, D.B, D.num_data = S, B, int(self.elbo.num_data)
         D.x, D.y, D.fid = x.data_ptr(), y.data_ptr(), f.data_ptr()
-        D.workspace = self._workspace(B, S).data_ptr()
+        D.workspace = self._workspace(B, S, pin=pin_workspace).data_ptr()
         D.accumulate = 1 if accumulate else 0
         _lib.check(self.lib.mobo_elbo_step(ctypes.byref(D), _lib.stream_ptr()), "mobo_elbo_step")
         self._last_inputs = keep          # keep the step's inputs alive until the next call (async kernels)
@@ -220,12 +240,23 @@ class FusedELBOStep(object):
         return self.out[0], self.out[1]
 
     def check(self):
-        """Synchronises and raises like upstream's NotPSDError / NanError when a Cholesky factorisation failed."""
-        st = float(self.out[3])
+        """Synchronises and raises like upstream's NotPSDError / NanError when ANY step since the last check failed:
+        a Cholesky factorisation that psd_safe_cholesky's three jitter retries could not rescue, or a non-finite ELBO.
+        The failing step's Adam update was skipped on the device (``skip_flag``), so the parameters are still the
+        ones that failed.  Called by the fitter at its reporting boundaries instead of once per step."""
+        o = self.out.tolist()
+        st = o[4] if o[4] != 0.0 else o[3]
         if st != 0.0:
-            raise RuntimeError("NotPSDError: K(Z, Z) + jitter I of layer %d is not positive definite" % (int(st) - 1))
-        if not bool(torch.isfinite(self.out[0])):
-            raise RuntimeError("NanError: the ELBO is not finite")
+            self.out[4:6].zero_()
+            raise NotPSDError("NotPSDError: K(Z, Z) + jitter I of layer %d is not positive definite (after the "
+                              "1e-8, 1e-7, 1e-6 jitter retries)" % (int(st) - 1))
+        if o[5] != 0.0 or o[0] != o[0] or o[0] in (float("inf"), float("-inf")):
+            self.out[4:6].zero_()
+            raise NanError("NanError: the ELBO is not finite")
+
+    def retries(self):
+        """psd_safe_cholesky retries the last step needed (0 .. 3); synchronises."""
+        return int(self.out[7])
 
 
 class Adam(torch.optim.Optimizer):
@@ -237,18 +268,21 @@ class Adam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self.capturable = capturable
-        self._step_dev = None
+        self._step_dev = None       # device-resident step count of the FIRST cohort of parameters (capturable)
+        self._cohorts = []          # one device count per set of parameters that joined in the same step() call
         self._tables = {}
+        # optional 1-element device tensor: != 0 -> the update is skipped on the device (FusedELBOStep.skip_flag:
+        # the step that produced the gradients hit NotPSDError / NanError, where upstream never reaches step())
+        self.skip_flag = None
 
     def zero_grad(self, set_to_none=False):
         # gradients live in a persistent flat buffer that the fused step overwrites: keep the tensors
         return super().zero_grad(set_to_none=set_to_none)
 
-    def _table(self, gi, chunk):
+    def _table(self, key, chunk):
         """ctypes table of (param, grad, exp_avg, exp_avg_sq, n) for a chunk of <= 64 parameters, rebuilt only when a
         pointer changes."""
         sig = tuple((p.data_ptr(), p.grad.data_ptr()) for p in chunk)
-        key = (gi, id(chunk[0]))
         hit = self._tables.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]
@@ -261,14 +295,56 @@ class Adam(torch.optim.Optimizer):
         self._tables[key] = (sig, arr)
         return arr
 
+    # ---- CUDA-graph capture support: warm-up and capture run real updates that must not count as training ----
+    @torch.no_grad()
+    def snapshot(self):
+        """Copies of the parameters and of every piece of optimiser state (moments, device step counts)."""
+        params = [p for g in self.param_groups for p in g["params"]]
+        snap = {"params": [(p, p.detach().clone()) for p in params], "state": [], "cohorts": len(self._cohorts),
+                "counts": [c.clone() for c in self._cohorts]}
+        for p in params:
+            st = self.state.get(p)
+            if st:
+                snap["state"].append((p, st["exp_avg"].clone(), st["exp_avg_sq"].clone(),
+                                      st["step"] if not torch.is_tensor(st["step"]) else None))
+        return snap
+
+    @torch.no_grad()
+    def restore(self, snap):
+        """Undo every update since ``snapshot`` in place (addresses baked into captured graphs stay valid): state
+        that existed is restored, state created since is zeroed."""
+        for p, v in snap["params"]:
+            p.copy_(v)
+        had = {id(p) for p, _, _, _ in snap["state"]}
+        for p, m, v, step in snap["state"]:
+            st = self.state[p]
+            st["exp_avg"].copy_(m); st["exp_avg_sq"].copy_(v)
+            if step is not None:
+                st["step"] = step
+        for p, _ in snap["params"]:
+            st = self.state.get(p)
+            if st and id(p) not in had:
+                st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+                if not torch.is_tensor(st["step"]):
+                    st["step"] = 0
+        for i, c in enumerate(self._cohorts):
+            if i < snap["cohorts"]:
+                c.copy_(snap["counts"][i])
+            else:
+                c.zero_()
+
     @torch.no_grad()
     def step(self, closure=None):
         if closure is not None:
             raise NotImplementedError("closures are not used by the reference's training loops")
         lib = _bind()
-        ticked = False
+        skip = None if self.skip_flag is None else _lib.ptr(self.skip_flag)
+        ticked = set()
+        new_cohort = None
         for gi, group in enumerate(self.param_groups):
-            ps = [p for p in group["params"] if p.grad is not None]
+            # frozen parameters are skipped even if a stale .grad survives from an earlier phase (torch's
+            # zero_grad(set_to_none=True) would have dropped it)
+            ps = [p for p in group["params"] if p.requires_grad and p.grad is not None]
             if not ps:
                 continue
             for p in ps:
@@ -277,33 +353,45 @@ class Adam(torch.optim.Optimizer):
                     if not (p.is_cuda and p.dtype == torch.float64 and p.is_contiguous() and p.grad.is_contiguous()):
                         raise RuntimeError("mobocmf_b200.Adam needs contiguous fp64 CUDA parameters (no CPU fallback)")
                     if self.capturable:
-                        if self._step_dev is None:
-                            self._step_dev = torch.zeros((), dtype=torch.int64, device=p.device)
-                        st["step"] = self._step_dev          # one shared device-resident count
+                        # parameters that join in the same call share one device-resident count; a parameter that
+                        # joins later starts its own (its bias correction must count ITS steps, like torch's
+                        # per-parameter `step`)
+                        if new_cohort is None:
+                            new_cohort = torch.zeros((), dtype=torch.int64, device=p.device)
+                            self._cohorts.append(new_cohort)
+                            if self._step_dev is None:
+                                self._step_dev = new_cohort
+                        st["step"] = new_cohort
                     else:
                         st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             b1, b2 = group["betas"]
             if self.capturable:
-                if not ticked:
-                    _lib.check(lib.mobo_adam_tick(_lib.ptr(self._step_dev), _lib.stream_ptr()), "mobo_adam_tick")
-                    ticked = True
-                for i in range(0, len(ps), 64):
-                    chunk = ps[i:i + 64]
-                    _lib.check(lib.mobo_adam(len(chunk), self._table(gi, chunk), float(group["lr"]), float(b1),
-                                             float(b2), float(group["eps"]), 0, _lib.ptr(self._step_dev),
-                                             _lib.stream_ptr()), "mobo_adam")
+                for ci, cnt in enumerate(self._cohorts):
+                    sel = [p for p in ps if self.state[p]["step"] is cnt]
+                    if not sel:
+                        continue
+                    if ci not in ticked:
+                        _lib.check(lib.mobo_adam_tick(_lib.ptr(cnt), skip, _lib.stream_ptr()), "mobo_adam_tick")
+                        ticked.add(ci)
+                    for i in range(0, len(sel), 64):
+                        chunk = sel[i:i + 64]
+                        _lib.check(lib.mobo_adam(len(chunk), self._table((gi, ci, i), chunk), float(group["lr"]),
+                                                 float(b1), float(b2), float(group["eps"]), 0, _lib.ptr(cnt), skip,
+                                                 _lib.stream_ptr()), "mobo_adam")
                 continue
             steps = {int(self.state[p]["step"]) for p in ps}
             for step0 in sorted(steps):
                 sel = [p for p in ps if int(self.state[p]["step"]) == step0]
                 for i in range(0, len(sel), 64):
                     chunk = sel[i:i + 64]
-                    _lib.check(lib.mobo_adam(len(chunk), self._table(gi, chunk), float(group["lr"]), float(b1),
-                                             float(b2), float(group["eps"]), step0 + 1, None, _lib.stream_ptr()),
-                               "mobo_adam")
+                    _lib.check(lib.mobo_adam(len(chunk), self._table((gi, "host", step0 - min(steps), i), chunk),
+                                             float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                             step0 + 1, None, skip, _lib.stream_ptr()), "mobo_adam")
                 for p in sel:
+                    # a skipped (failed) step still counts here: the host cannot know without a synchronisation, and
+                    # the failure is raised at the next FusedELBOStep.check() anyway
                     self.state[p]["step"] = step0 + 1
         return None
 
@@ -320,6 +408,7 @@ class GraphedELBOStep(object):
         if not isinstance(optimizer, Adam) or not optimizer.capturable:
             raise ValueError("GraphedELBOStep needs mobocmf_b200.fused.Adam(capturable=True)")
         self.step, self.optimizer, self.S = step, optimizer, int(num_samples)
+        optimizer.skip_flag = step.skip_flag
         dev, d = step.device, step.d
         # static_eps: the caller supplies the training normals on every call (parity tests); otherwise they are drawn
         # inside the graph
@@ -336,28 +425,24 @@ class GraphedELBOStep(object):
     def _capture(self):
         # parameters are NOT stepped during warm-up / capture side effects: snapshot and restore them and the
         # optimiser state, so that capturing does not count as training steps
-        params = [p for g in self.optimizer.param_groups for p in g["params"]]
-        snap = [p.detach().clone() for p in params]
+        snap = self.optimizer.snapshot()
+        out_keep = self.step.out.clone()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(self._warmup):
-                self.step(self.x, self.y, self.f, eps=self.eps, num_samples=self.S, check_shortcut=False)
+                self.step(self.x, self.y, self.f, eps=self.eps, num_samples=self.S, check_shortcut=False,
+                          pin_workspace=True)
                 self.optimizer.step()
         torch.cuda.current_stream().wait_stream(s)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss, self.kl = self.step(self.x, self.y, self.f, eps=self.eps, num_samples=self.S,
-                                           check_shortcut=False)
+                                           check_shortcut=False, pin_workspace=True)
             self.optimizer.step()
+        self.optimizer.restore(snap)
         with torch.no_grad():
-            for p, v in zip(params, snap):
-                p.copy_(v)
-            for p in params:
-                st = self.optimizer.state.get(p)
-                if st:
-                    st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
-            self.optimizer._step_dev.zero_()
+            self.step.out.copy_(out_keep)      # sticky status flags: staging data of the warm-up steps does not count
 
     def _stage(self, x_batch, y_batch, fidelities, eps):
         self.x.copy_(x_batch); self.y.copy_(y_batch.reshape(-1, 1)); self.f.copy_(fidelities.reshape(-1, 1))
@@ -367,8 +452,8 @@ class GraphedELBOStep(object):
             for l in range(1, self.step.L):
                 self.eps[l].copy_(eps[l].reshape(-1))
 
-    def __call__(self, x_batch, y_batch, fidelities, eps=None):
-        if not self.step.applies(x_batch):
+    def __call__(self, x_batch, y_batch, fidelities, eps=None, check_shortcut=True):
+        if check_shortcut and not self.step.applies(x_batch):
             raise RuntimeError("x_batch equals the inducing inputs (quirk Q4 shortcut): use the composable path")
         if self.graph is None:
             self._stage(x_batch, y_batch, fidelities, eps)

@@ -105,9 +105,22 @@ class _GraphedConditionedStep(object):
         fitter.pareto_front = fitter.pareto_front.to(dev)
         fitter.thresholds_cons = fitter.thresholds_cons.to(dev)
         self.x_tilde = torch.zeros(10, fitter.pareto_set.shape[1], dtype=torch.float64, device=dev)
-        self.static = None
-        self.graph = None
-        self.loss = None
+        # The upstream `torch.equal(x, Z)` shortcut (quirk Q4) is a device comparison = a synchronisation, illegal
+        # inside a capture.  It can only fire for an input with Z's shape (N == pareto_set_size or N == 10 rows do
+        # happen): answer it HERE, once, on the host.  x-tilde is redrawn uniformly every iteration and never equals
+        # Z; the Pareto set is fixed, so one comparison per model settles it (if it does equal some model's Z the
+        # arithmetic changes and the iteration stays eager).
+        self.x_tilde._mobo_not_z = True
+        ps_host = fitter.pareto_set.detach().cpu()
+        self.capturable = True
+        for h in self.handlers:
+            z = getattr(h.mfdgp, h.mfdgp.name_hidden_layer + "0")._Zx().detach().cpu()
+            if z.shape == ps_host.shape and bool(torch.equal(z, ps_host)):
+                self.capturable = False
+        if self.capturable:
+            fitter.pareto_set._mobo_not_z = True
+        self.graphs = {}       # minibatch shapes -> (static buffers, graph, loss): the ragged last batch of an epoch
+        #                        gets its own graph (the reference's DataLoader yields it like any other)
 
     def _fetch(self):
         out = {}
@@ -125,23 +138,9 @@ class _GraphedConditionedStep(object):
                 return True
         return False
 
-    def _stage(self, batches):
-        if self.static is None:
-            self.static = {}
-            for key in self.keys:
-                bufs = tuple(t.detach().clone() for t in batches[key])
-                bufs[0]._mobo_not_z = True          # checked on the host for every minibatch (_hits_shortcut)
-                self.static[key] = bufs
-            return
-        for key in self.keys:
-            for dst, src in zip(self.static[key], batches[key]):
-                if dst.shape != src.shape:
-                    raise RuntimeError("the captured conditioned step needs minibatches of constant shape")
-                dst.copy_(src)
-
-    def _iteration(self):
+    def _iteration(self, static):
         self.x_tilde.uniform_()
-        loss = self.fitter.conditioned_loss(self.hs_o, self.hs_c, x_tilde=self.x_tilde, batches=self.static)
+        loss = self.fitter.conditioned_loss(self.hs_o, self.hs_c, x_tilde=self.x_tilde, batches=static)
         loss.backward()
         self.optimizer.step()
         return loss.detach()
@@ -152,47 +151,48 @@ class _GraphedConditionedStep(object):
             for i in range(m.num_hidden_layers):
                 yield getattr(m, m.name_hidden_layer + str(i))
 
-    def _capture(self):
-        params = [p for g in self.optimizer.param_groups for p in g["params"]]
-        snap = [p.detach().clone() for p in params]
+    def _capture(self, batches):
+        static = {}
+        for key in self.keys:
+            bufs = tuple(t.detach().clone() for t in batches[key])
+            bufs[0]._mobo_not_z = True          # checked on the host for every minibatch (_hits_shortcut)
+            static[key] = bufs
+        snap = self.optimizer.snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(self.warmup):
                 self.optimizer.zero_grad(set_to_none=True)
-                self._iteration()
+                self._iteration(static)
         torch.cuda.current_stream().wait_stream(side)
         self.optimizer.zero_grad(set_to_none=True)
         for layer in self._layers():
             layer._ops_cache = None
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._iteration()
-        with torch.no_grad():       # warm-up and capture do not count as training iterations
-            for p, v in zip(params, snap):
-                p.copy_(v)
-            for p in params:
-                st = self.optimizer.state.get(p)
-                if st:
-                    st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
-            if self.optimizer._step_dev is not None:
-                self.optimizer._step_dev.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self._iteration(static)
+        self.optimizer.restore(snap)    # warm-up and capture do not count as training iterations
+        return static, graph, loss
 
     def __call__(self):
         batches = self._fetch()
-        if self._hits_shortcut(batches):
+        if not self.capturable or self._hits_shortcut(batches):
             self.optimizer.zero_grad()
             loss = self.fitter.conditioned_loss(self.hs_o, self.hs_c, batches=batches)
             loss.backward()
             self.optimizer.step()
             return loss.detach()
-        self._stage(batches)
-        if self.graph is None:
-            self._capture()
-        self.graph.replay()
+        shape_key = tuple(tuple(t.shape) for key in self.keys for t in batches[key])
+        if shape_key not in self.graphs:
+            self.graphs[shape_key] = self._capture(batches)
+        static, graph, loss = self.graphs[shape_key]
+        for key in self.keys:
+            for dst, src in zip(static[key], batches[key]):
+                dst.copy_(src)
+        graph.replay()
         for layer in self._layers():
             layer._ops_cache = None       # the cached operators belong to the graph's memory pool
-        return self.loss
+        return loss
 
 
 class BlackBoxMFDGPFitter():
@@ -286,16 +286,22 @@ class BlackBoxMFDGPFitter():
         kl_iter = 0.0
         fused = BlackBoxMFDGPFitter._fused_step(model, elbo)
         graphed = fused is not None and getattr(optimizer, "capturable", False) and eps is None
+        guarded = isinstance(optimizer, Adam)
         for (x_batch, y_batch, fidelities) in train_loader:
-            if graphed and fused.applies(x_batch):
+            use_fused = fused is not None and fused.applies(x_batch)
+            if guarded:
+                # a fused step that fails (NotPSDError / NanError upstream) must not reach the parameters: its Adam
+                # update is skipped on the device; the error itself is raised at the next reporting boundary
+                optimizer.skip_flag = fused.skip_flag if use_fused else None
+            if graphed and use_fused:
                 loss, kl = BlackBoxMFDGPFitter._graphed_step(fused, optimizer, x_batch.shape[0])(
-                    x_batch, y_batch, fidelities)            # forward, ELBO, backward AND the Adam update
+                    x_batch, y_batch, fidelities, check_shortcut=False)   # forward, ELBO, backward AND the Adam update
                 loss_iter += loss.detach().clone()
                 kl_iter += kl.detach().clone()
                 continue
-            if fused is not None and fused.applies(x_batch):
+            if use_fused:
                 # forward, ELBO and backward in one enqueue; gradients are overwritten, so no zero_grad
-                loss, kl = fused(x_batch, y_batch, fidelities, eps=eps)
+                loss, kl = fused(x_batch, y_batch, fidelities, eps=eps, check_shortcut=False)
                 optimizer.step()
                 loss_iter += loss.detach().clone()
                 kl_iter += kl.detach().clone()
@@ -320,10 +326,14 @@ class BlackBoxMFDGPFitter():
             hs = list(handlers.values())
 
             def report(n, i, loss_iter, kl_iter):
-                if self.verbose and ((i % ITER_PRINT) == 0 or ((i + 1) == num_epochs)):
-                    print("[%s: " % kind, n, "] Epoch:", i, "/", num_epochs, ". Avg. Neg. ELBO per epoch:",
-                          loss_iter.item(), "\t KL per epoch:", kl_iter.item())
-                    sys.stdout.flush()
+                if (i % ITER_PRINT) == 0 or ((i + 1) == num_epochs):
+                    # the only place the training loop synchronises: surface NotPSDError / NanError of any step
+                    # since the last boundary (upstream raises inside the step)
+                    self._check_status(hs[n])
+                    if self.verbose:
+                        print("[%s: " % kind, n, "] Epoch:", i, "/", num_epochs, ". Avg. Neg. ELBO per epoch:",
+                              loss_iter.item(), "\t KL per epoch:", kl_iter.item())
+                        sys.stdout.flush()
 
             if self.concurrent_models and len(hs) > 1:
                 cur = torch.cuda.current_stream(hs[0].device)
@@ -342,6 +352,14 @@ class BlackBoxMFDGPFitter():
                 for i in range(num_epochs):
                     loss_iter, kl_iter = func_update_model(h.mfdgp, h.elbo, optimizer, h.train_loader)
                     report(n, i, loss_iter, kl_iter)
+
+    @staticmethod
+    def _check_status(handler):
+        from .. import functional as F
+        fused = getattr(handler.elbo, "_fused_step", None)
+        if fused:
+            fused.check()
+        F.check_status(handler.device)
 
     def train_mfdgps(self):
         self._train_mfdgp(self._update_model, fix_variational_hypers=True, num_epochs=self.num_epochs_1,
@@ -488,6 +506,8 @@ class BlackBoxMFDGPFitter():
                 cache[id(optimizer)] = _GraphedConditionedStep(self, handlers_objs, handlers_cons, optimizer)
             return cache[id(optimizer)]()
         optimizer.zero_grad()
+        if isinstance(optimizer, Adam):
+            optimizer.skip_flag = None
         loss = self.conditioned_loss(handlers_objs, handlers_cons)
         loss.backward()
         optimizer.step()
@@ -502,9 +522,15 @@ class BlackBoxMFDGPFitter():
         for i in range(num_iters):
             loss_iter = func_update_model(self.mfdgp_handlers_objs.values(), self.mfdgp_handlers_cons.values(),
                                           optimizer)
-            if self.verbose and ((i % ITER_PRINT) == 0 or ((i + 1) == num_iters)):
-                print("Iter:", i, "/", num_iters, ". Neg. ELBO per iter:", loss_iter.item())
-                sys.stdout.flush()
+            if (i % ITER_PRINT) == 0 or ((i + 1) == num_iters):
+                from .. import functional as F
+                F.check_status()
+                if not bool(torch.isfinite(loss_iter)):
+                    from ..errors import NanError
+                    raise NanError("NanError: the conditioned loss is not finite")
+                if self.verbose:
+                    print("Iter:", i, "/", num_iters, ". Neg. ELBO per iter:", loss_iter.item())
+                    sys.stdout.flush()
 
     def train_conditioned_mfdgps(self):
         self._train_conditioned_mfdgps(self._update_conditioned_models, fix_variational_hypers=True,

@@ -69,12 +69,29 @@ class FlatGrads(object):
 
 
 def broadcast_parameters(module, src=0, group=None):
-    """Make every rank start from rank ``src``'s parameters and buffers (model construction draws random eval
-    samples, layers/mfdgp_hidden_layer.py:161)."""
+    """Make every rank start from rank ``src``'s parameters, buffers AND fixed eval-mode normals.  The latter are
+    drawn at construction (``samples``, layers/mfdgp_hidden_layer.py:161) and are a plain attribute, not a buffer
+    (as in the reference, so that state_dicts stay compatible): without this, ranks that were seeded differently
+    would evaluate their acquisition shards with different normals and ``gather_candidate_values`` /
+    ``argmax_over_ranks`` would compare inconsistent values."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+    for sub in module.modules():
+        smp = getattr(sub, "samples", None)
+        if torch.is_tensor(smp):
+            if dist.get_backend(group) == "nccl" and not smp.is_cuda:
+                dev = next((p.device for p in module.parameters() if p.is_cuda), None)
+                buf = smp.to(dev)
+                dist.broadcast(buf, src=src, group=group)
+                smp.copy_(buf.cpu())
+            else:
+                dist.broadcast(smp, src=src, group=group)
+            cache = getattr(sub, "_dev_cache", None)
+            if isinstance(cache, dict):          # device copies of the old samples
+                for k in [k for k in cache if isinstance(k, tuple) and k and k[0] == "samples"]:
+                    del cache[k]
 
 
 def gather_candidate_values(local_values, n_total, group=None):

@@ -256,4 +256,4 @@ def test_cuda_graph_replay_matches_eager_steps():
         assert relerr(l1, l2) < 1e-12, (it, relerr(l1, l2))
     for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
         assert relerr(a, b) < 1e-12, (n, relerr(a, b))
-    assert int(o1._step_dev) == 6
+    assert int(o1._step_dev) == 6 and len(o1._cohorts) == 1

@@ -1,0 +1,96 @@
+"""CPU: the extended-precision truth (oracle/mfdgp_truth.py over oracle/ld_autodiff.py, numpy longdouble) pinned against
+the fp64 oracle and torch autograd on well-conditioned inputs, where fp64 itself is accurate to ~1e-13; and shown to
+be the better answer on ill-conditioned ones (the fp64 oracle's two formulations of the same quantity bracket it)."""
+import numpy as np
+import torch
+
+from oracle import ld_autodiff as A
+from oracle import mfdgp_oracle as O
+from oracle import mfdgp_truth as T
+from tests.helpers import clone_state, param_keys, random_state
+
+
+def _case(M, d, L, B, S, ls, seed=0):
+    sd, up = random_state(M, d, L, seed=seed, ls=ls)
+    g = torch.Generator().manual_seed(seed + 11)
+    x = torch.rand(B, d, generator=g, dtype=torch.float64)
+    y = torch.randn(B, 1, generator=g, dtype=torch.float64)
+    fid = torch.randint(0, L, (B, 1), generator=g).double()
+    eps = [None] + [torch.randn(B * S, generator=g, dtype=torch.float64) for _ in range(1, L)]
+    return sd, up, x, y, fid, eps
+
+
+def test_autodiff_primitives_against_torch():
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(6, 6, generator=g, dtype=torch.float64)
+    spd = (a @ a.T + 6 * torch.eye(6, dtype=torch.float64)).requires_grad_(True)
+    b = torch.randn(6, 4, generator=g, dtype=torch.float64, requires_grad=True)
+    Lt = torch.linalg.cholesky(spd)
+    out_t = (torch.cholesky_solve(b, Lt) ** 2).sum() + Lt.diagonal().log().sum() + \
+        torch.linalg.solve_triangular(Lt, b, upper=False).exp().sum()
+    out_t.backward()
+    sv, bv = A.leaf(spd), A.leaf(b)
+    L = A.cholesky(sv)
+    idx = np.arange(6)
+    out = A.sum_(A.square(A.solve_lower_t(L, A.solve_lower(L, bv)))) + A.sum_(A.log(L[idx, idx])) + \
+        A.sum_(A.exp(A.solve_lower(L, bv)))
+    A.backward(out)
+    assert abs(float(out.v) - float(out_t)) < 1e-12 * abs(float(out_t))
+    # torch returns the gradient w.r.t. the symmetric input as is; both sides symmetrise identically
+    gs = (spd.grad + spd.grad.T) / 2
+    assert T.err_vs(gs, (sv.g + sv.g.T) / 2) < 1e-12
+    assert T.err_vs(b.grad, bv.g) < 1e-12
+
+
+def test_truth_matches_oracle_on_well_conditioned_step():
+    L, S, B = 3, 3, 20
+    sd, up, x, y, fid, eps = _case(24, 2, L, B, S, ls=0.08)
+    names = param_keys(sd)
+    sdo = clone_state(sd, requires_grad=True)
+    loss_o, kl_o = O.elbo_step_loss_tiled(sdo, L, up, x, y, fid, eps, 3 * B, S)
+    loss_o.backward()
+    loss_t, kl_t, grads = T.elbo_step_truth(sd, names, L, up, x, y, fid, eps, 3 * B, S)
+    assert T.err_vs(loss_o, loss_t) < 1e-13 and T.err_vs(kl_o, kl_t) < 1e-13
+    for n in names:
+        go = sdo[n].grad
+        gt = grads[n]
+        if "chol_variational_covar" in n:
+            go, gt = torch.tril(go), np.tril(gt)
+        assert T.err_vs(go, gt) < 1e-11, (n, T.err_vs(go, gt))
+
+
+def test_truth_jes_and_dx_match_oracle():
+    L = 2
+    sd, up = random_state(20, 2, L, seed=3, ls=0.1)
+    sdc = {k: v.clone() for k, v in sd.items()}
+    sdc["hidden_layer_1.variational_strategy._variational_distribution.chol_variational_covar"] *= 0.6
+    g = torch.Generator().manual_seed(5)
+    samples = [torch.randn(7, 1, generator=g) for _ in range(L)]
+    X = torch.rand(9, 1, 2, generator=g, dtype=torch.float64, requires_grad=True)
+    mods = [dict(sd=s, num_layers=L, noise_upper=up, samples=samples) for s in (sd, sdc)]
+    val_o = O.jes_mfdgp(mods[0], mods[1], X, 1)
+    val_o.sum().backward()
+    val_t, dx_t = T.jes_truth(mods[0], mods[1], X.detach(), 1)
+    assert float(val_o.max()) > 1e-4
+    assert T.err_vs(val_o, val_t) < 1e-11
+    assert T.err_vs(X.grad.reshape(9, 2), dx_t) < 1e-9
+
+
+def test_truth_adjudicates_ill_conditioned_case():
+    """Reference-default-like lengthscales: cond(P) ~ 1e7.  The fp64 oracle is then a few 1e-9 .. 1e-6 from the truth
+    in the gradients - the band the CUDA path is allowed (tests/test_gpu_*: |cuda - truth| <= 10 |oracle - truth|)."""
+    L, S, B = 2, 2, 30
+    sd, up, x, y, fid, eps = _case(40, 2, L, B, S, ls=0.9)
+    Z = O.layer_inducing_points(sd, 0)
+    cond = float(torch.linalg.cond(O.layer_kernel(sd, 0, Z, Z) + 1e-6 * torch.eye(40, dtype=torch.float64)))
+    assert cond > 1e6
+    names = param_keys(sd)
+    sdo = clone_state(sd, requires_grad=True)
+    loss_o, _ = O.elbo_step_loss_tiled(sdo, L, up, x, y, fid, eps, 3 * B, S)
+    loss_o.backward()
+    loss_t, _, grads = T.elbo_step_truth(sd, names, L, up, x, y, fid, eps, 3 * B, S)
+    worst = max(T.err_vs(torch.tril(sdo[n].grad) if "chol_var" in n else sdo[n].grad,
+                         np.tril(grads[n]) if "chol_var" in n else grads[n]) for n in names)
+    print("cond %.1e  loss err %.1e  worst grad err of the fp64 oracle %.1e" % (cond, T.err_vs(loss_o, loss_t), worst))
+    assert T.err_vs(loss_o, loss_t) < 1e-6 and worst < 1e-2      # the oracle is a correct fp64 program ...
+    assert worst > 1e-13                                          # ... whose rounding error the truth resolves
