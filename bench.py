@@ -4,11 +4,15 @@
 Workload (BASELINE.json configs[3], SURVEY.md §8d "C4"): scaled MFDGP training, d=6, 3 fidelities, N=50 000
 synthetic points, M=256 inducing inputs, minibatch B=1024 rows x S=64 MC samples, fp64.  One STEP = the body of
 ``_update_model`` (mobocmf/util/blackbox_mfdgp_fitter.py:161-171): zero-grad, forward, ELBO, backward, Adam.
-With N GPUs every rank processes its own 1024-row minibatch (weak scaling) and the parameter gradients are summed
-with one NCCL all-reduce, i.e. one global step over N*1024 rows; ``value`` counts 1024-row step units per second.
+``--scaling weak`` (default): with N GPUs every rank processes its own 1024-row minibatch and the parameter gradients
+are summed over NCCL, i.e. one global step over N*1024 rows; ``value`` counts 1024 x 64 step units per second.
+``--scaling strong``: ONE 1024 x 64 step whose rows are split over the ranks (``util.distributed.shard_bounds``);
+``value`` counts global steps per second.
 
-The second headline of BASELINE.json (JESMOC acquisition evals/s, configs[4] "C5") is measured on a slice and
-reported under ``"acq"`` in the same JSON line.
+The second headline of BASELINE.json (JESMOC acquisition evals/s, configs[4] "C5": 10^6 candidates x 16 Pareto samples
+x (4 objectives + 2 constraints) sharded over 8 GPUs = 125 000 candidates per GPU) is reported under ``"acq"`` in the
+same JSON line with its own roofline / cpu_baseline / e2e blocks; ``"parity"`` holds the CUDA-vs-oracle errors of
+one C4 step, computed outside the timed region.
 """
 import argparse
 import json
@@ -25,6 +29,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 C4 = dict(N=50000, d=6, L=3, M=256, B=1024, S=64, fid_sizes=(30000, 15000, 5000), lengthscale=0.3, seed=0)
+C5_CANDIDATES_PER_GPU = 125000   # 10^6 candidates over 8 GPUs (BASELINE.json configs[4])
+
+
+def workload_config(world, scaling, B):
+    """``config`` of the JSON line, shared by both arms (the reference arm times the same workload on the host)."""
+    per = "per GPU (step unit = 1024 x 64)" if scaling == "weak" else "in total, rows sharded over the GPUs"
+    return {"workload": "C4 scaled MFDGP training: d=6, 3 fidelities, N=50000, M=256, B=1024 rows x S=64 MC samples "
+                        "%s, lengthscale 0.3, Adam lr 1e-3" % per,
+            "global_batch": world * B if scaling == "weak" else B,
+            "parallelism": "dp%d rows sharded, grads all-reduced" % world,
+            "cache": "per-step working set (3 x 134 MB saved tiles per upper layer) exceeds L2"}
 FP64_PEAK_TFLOPS = 37.1   # measured DMMA.8x8x4 pipe peak on this pool's B200 (profiles/r01_fp64_probe.log);
 #                           cuBLAS DGEMM reaches 35.4 (profiles/r01_dgemm_probe.log).  MEASURED_PEAKS.json has no fp64 entry.
 
@@ -110,8 +125,18 @@ def run_ours(args):
     model.fix_variational_hypers(False)
     params = [p for p in model.parameters() if p.requires_grad]
     xd, yd, fd = x.to(dev), y.to(dev), fid.to(dev)
-    B, S, N = cfg["B"], cfg["S"], cfg["N"]
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    S, N = cfg["S"], cfg["N"]
+    strong = args.scaling == "strong"
+    if strong:
+        # ONE global minibatch of cfg["B"] points per step, drawn identically on every rank; rank r owns a contiguous
+        # shard of its points (and their S sample rows)
+        from mobocmf_b200.util.distributed import shard_bounds
+        lo_b, hi_b = shard_bounds(cfg["B"], rank, world)
+        B = hi_b - lo_b
+    else:
+        lo_b, B = 0, cfg["B"]
+    Bdraw = cfg["B"]
+    g = torch.Generator(device=dev).manual_seed(1234 + (0 if strong else rank))
     # pinned host staging for the end-to-end arm
     xh, yh, fh = x.pin_memory(), y.pin_memory(), fid.pin_memory()
 
@@ -152,14 +177,14 @@ def run_ours(args):
             return loss
 
     def device_step():
-        idx = torch.randint(0, N, (B,), device=dev, generator=g)
+        idx = torch.randint(0, N, (Bdraw,), device=dev, generator=g)[lo_b:lo_b + B]
         return one_step(xd[idx], yd[idx], fd[idx])
 
     # two pinned staging sets: the host fills set i % 2 while the copies of step i - 1 may still be in flight; set
     # i % 2 was last used by step i - 2, whose loss has been consumed (so its copies are complete) by then
     hbs = [[torch.empty(B, cfg["d"], dtype=torch.float64).pin_memory(), torch.empty(B, 1, dtype=torch.float64).pin_memory(),
             torch.empty(B, 1, dtype=torch.float64).pin_memory()] for _ in range(2)]
-    gh = torch.Generator().manual_seed(99 + rank)
+    gh = torch.Generator().manual_seed(99 + (0 if strong else rank))
 
     # End-to-end arm: every step copies ITS minibatch from pinned host memory (H2D inside the timed region) and the
     # step's loss comes back to pinned host memory (D2H).  The loss of step i is consumed by the host while step
@@ -172,7 +197,7 @@ def run_ours(args):
     def e2e_step():
         slot = len(e2e_losses) % 2
         hb = hbs[slot]
-        idx = torch.randint(0, N, (B,), generator=gh)
+        idx = torch.randint(0, N, (Bdraw,), generator=gh)[lo_b:lo_b + B]
         torch.index_select(xh, 0, idx, out=hb[0]); torch.index_select(yh, 0, idx, out=hb[1])
         torch.index_select(fh, 0, idx, out=hb[2])
         xb, yb, fb = (t.to(dev, non_blocking=True) for t in hb)
@@ -210,6 +235,10 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
+
+    parity = None
+    if rank == 0 and not args.no_parity and args.path == "fused":
+        parity = parity_block(cfg, x, y, fid, model, fstep, dev)
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -261,28 +290,28 @@ def run_ours(args):
     # acquisition slice (C5-shaped): n candidates x S=25 samples through an (uncond, cond) pair at the top fidelity
     acq = None
     if not args.no_acq:
-        acq = bench_acq(model, dev, cfg, world)
+        acq = bench_acq(model, dev, cfg, world, rank, n=args.acq_candidates, with_cpu=not args.no_cpu)
 
     if rank == 0:
         flops, f1 = step_flops(cfg)
         ms_step = ms / args.steps
+        units = 1 if strong else world          # 1024 x 64 step units completed per timed step
         out = {
-            "metric": "mfdgp_elbo_steps_per_s", "value": world * args.steps / (ms / 1e3), "unit": "steps/s",
+            "metric": "mfdgp_elbo_steps_per_s", "value": units * args.steps / (ms / 1e3), "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C4 scaled MFDGP training: d=6, 3 fidelities, N=50000, M=256, B=1024 rows x S=64 "
-                                   "MC samples per GPU (step unit = 1024 x 64), lengthscale 0.3, Adam lr 1e-3",
-                       "global_batch": world * B, "parallelism": "dp%d rows sharded, grads all-reduced" % world,
-                       "cache": "per-step working set (3 x 134 MB saved tiles per upper layer) exceeds L2"},
-            "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": "steps/s",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(world, args.scaling, cfg["B"]),
+            "e2e": {"value": units * args.steps / (ms_e2e / 1e3), "unit": "steps/s",
                     "h2d_bytes_per_step": B * (cfg["d"] + 2) * 8, "d2h_bytes_per_step": 8,
                     "losses_finite": e2e_finite, "last_loss": e2e_losses[-1],
                     "note": "host minibatch -> pinned H2D -> fused step + Adam -> loss D2H, every step; the loss of "
                             "step i is read while step i+1 is enqueued"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary() if sampler else None,
-            "step_tflops": flops / (ms_step * 1e-3) / 1e12,
+            "step_tflops": flops / (ms_step * 1e-3) / 1e12 * (1 if not strong else 1.0 / world),
         }
+        if parity is not None:
+            out["parity"] = parity
         if prof:
             tot = {k: sum(v) for k, v in prof.items()}
             nst = min(args.steps, 5)
@@ -290,7 +319,7 @@ def run_ours(args):
             # summed over its launches of a step (layer 0 runs on B rows, the upper layers on B*S) and divided by the
             # summed launch durations (DESIGN.md section 2 "Roofline numerator")
             M, d, L = cfg["M"], cfg["d"], cfg["L"]
-            rows = [B] + [B * S] * (L - 1)
+            rows = [B] + [B * S] * (L - 1)       # this rank's rows (strong scaling: its shard)
             dl = [d] + [d + 1] * (L - 1)
             alg_per_step = {
                 "row_fwd_kernel": sum(r * (2 * M * M + 2 * M + 3 * k * M) for r, k in zip(rows, dl)),
@@ -323,7 +352,7 @@ def run_ours(args):
         if not args.no_acq and world == 1:
             out["small_configs"] = bench_small_configs(dev)
         if not args.no_cpu and world == 1:      # reported on rank 0 at N = 1 only
-            out["cpu_baseline"] = cpu_baseline(cfg, x, y, fid, model, max_seconds=25.0, steps=10, warmup=2)
+            out["cpu_baseline"] = cpu_baseline(cfg, x, y, fid, model, steps=8, warmup=2)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -466,81 +495,181 @@ def bench_conditioned(dev, x, y, fid, iters=100):
     return out
 
 
-def bench_acq(model, dev, cfg, world, n=8192, K=6, P=16, iters=2):
-    """JESMOC acquisition sweep, BASELINE.json configs[4] (SURVEY.md section 8d "C5") on a slice: every rank evaluates
-    ITS n candidates (candidates shard across GPUs, no data-path collective) through the full coupled acquisition:
-    K = 6 black boxes (4 objectives + 2 constraints) x (1 unconditioned + P = 16 Pareto-conditioned) MFDGPs = 102 model
-    chains per candidate, each S = 25 samples through 3 layers (1 + 25 + 25 rows, M = 256):
-        acq(x) = 1/P sum_p sum_k 1/2 max(0, log v_u,k(x) - log v_c,k,p(x))
-    (mobocmf/acquisition_functions/JESMOC_MFDGP.py:38-52,125-135; P > 1 = average of P single-sample acquisitions,
-    SURVEY.md fact F5).  One 'eval' = one candidate through all 102 chains.  Models are random perturbations of the
-    bench model (timing does not depend on the parameter values)."""
+def acq_models(model, dev, K=6, P=16):
+    """K black boxes x (1 unconditioned + P Pareto-conditioned) MFDGPs: seeded perturbations of the bench model (cond
+    params = uncond + perturbation of m and L_q; timing does not depend on the values)."""
     import copy
-    import torch.distributed as dist
-    from mobocmf_b200 import _lib
-    fidelity = cfg["L"] - 1
     g = torch.Generator(device=dev).manual_seed(7)
-    unc, cond = [], []
+    boxes = []
     for k in range(K):
         u = copy.deepcopy(model)
         with torch.no_grad():
             for nme, p in u.named_parameters():
                 if "variational_mean" in nme:
                     p.add_(0.05 * torch.randn(p.shape, generator=g, device=dev, dtype=p.dtype))
-        u.eval()
-        unc.append(u)
-        row = []
+        conds = []
         for pp in range(P):
             c = copy.deepcopy(u)
             with torch.no_grad():
                 for nme, p in c.named_parameters():
                     if "chol_variational_covar" in nme:
                         p.mul_(0.6 + 0.3 * (pp + 1) / P)
-            c.eval()
-            row.append(c)
-        cond.append(row)
-    X = torch.rand(n, cfg["d"], device=dev, dtype=torch.float64, generator=g)
-    lib = _lib.load()
-    out = torch.zeros(n, dtype=torch.float64, device=dev)
+            conds.append(c)
+        boxes.append((u, conds))
+    return boxes
 
-    def sweep():
-        out.zero_()
-        with torch.no_grad():
-            for k in range(K):
-                _, vu = unc[k].predict_for_acquisition(X, fidelity)
-                unc[k].eval()
-                for pp in range(P):
-                    _, vc = cond[k][pp].predict_for_acquisition(X, fidelity)
-                    cond[k][pp].eval()
-                    _lib.check(lib.mobo_jes(_lib.ptr(vu), _lib.ptr(vc), n, 1, _lib.ptr(out), _lib.stream_ptr()),
-                               "mobo_jes")
-            out.div_(P)
-        return out
 
-    sweep()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+def acq_flop_per_candidate(cfg, K, P, S=25):
+    """per candidate and model chain 1 layer-0 row + S rows in each of the L - 1 upper layers,
+    F = 2 M^2 + 2 M + 3 d_l M flop per row; K (1 + P) chains -> 7.1e8 flop per candidate at C5."""
+    M, d, L = cfg["M"], cfg["d"], cfg["L"]
+    f0 = 2 * M * M + 2 * M + 3 * d * M
+    f1 = 2 * M * M + 2 * M + 3 * (d + 1) * M
+    return K * (1 + P) * (f0 + (L - 1) * S * f1)
+
+
+def bench_acq(model, dev, cfg, world, rank, n=C5_CANDIDATES_PER_GPU, K=6, P=16, iters=1, with_cpu=True, n_grad=1024):
+    """JESMOC acquisition sweep, BASELINE.json configs[4] (SURVEY.md section 8d "C5"): every rank evaluates ITS n
+    candidates (10^6 over 8 GPUs = 125 000 per GPU; candidates shard, no data-path collective) through the full coupled
+    acquisition: K = 6 black boxes (4 objectives + 2 constraints) x (1 unconditioned + P = 16 Pareto-conditioned) MFDGPs
+    = 102 model chains per candidate, each S = 25 samples through 3 layers (1 + 25 + 25 rows, M = 256), evaluated at
+    the top fidelity:
+        acq(x) = 1/P sum_p sum_k 1/2 max(0, log v_u,k(x) - log v_c,k,p(x))
+    (mobocmf/acquisition_functions/JESMOC_MFDGP.py:38-52,125-135; mobocmf_b200...JESMOC_MFDGP.jes_sweep).  One 'eval'
+    = one candidate through all 102 chains.  Legs: device-resident forward (value), end to end from pinned host
+    memory (e2e), forward + d/dX on n_grad candidates (what optimize_acqf consumes), the CPU oracle on a bounded slice
+    (rank 0, N = 1)."""
+    import torch.distributed as dist
+    from mobocmf_b200.acquisition_functions.JESMOC_MFDGP import jes_sweep
+    fidelity = cfg["L"] - 1
+    boxes = acq_models(model, dev, K, P)
+    g = torch.Generator().manual_seed(1 + rank)
+    Xh = torch.rand(n, cfg["d"], dtype=torch.float64, generator=g).pin_memory()
+    X = Xh.to(dev)
+
+    def sync_max(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    jes_sweep(X[:4096], fidelity, boxes)          # warm-up: operator buffers of the 102 models, allocator, kernels
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        sweep()
+        out = jes_sweep(X, fidelity, boxes)
     e1.record()
+    barrier()
+    ms = sync_max(e0.elapsed_time(e1) / iters)
+
+    # end to end: candidates from pinned host memory, values back to pinned host memory, host waits for them
+    vals_h = torch.empty(n, dtype=torch.float64).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    Xd = Xh.to(dev, non_blocking=True)
+    vals_h.copy_(jes_sweep(Xd, fidelity, boxes), non_blocking=True)
     torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms)
+    ms_e2e = sync_max((time.perf_counter() - t0) * 1e3)
+    same = bool(torch.equal(vals_h, out.cpu()))
+
+    # forward + d acq / dX (autograd over the composable kernels; saved whitened rows of all chains stay alive until
+    # the backward, which bounds the candidate count of this leg)
+    Xg = X[:n_grad].clone().requires_grad_(True)
+    jes_sweep(Xg, fidelity, boxes).sum().backward()
+    Xg.grad = None
+    barrier()
+    e0.record()
+    v = jes_sweep(Xg, fidelity, boxes)
+    v.sum().backward()
+    e1.record()
+    barrier()
+    ms_g = sync_max(e0.elapsed_time(e1))
+    grad_ok = bool(torch.isfinite(Xg.grad).all()) and float(Xg.grad.abs().max()) > 0.0
+    fwd_vs_grad = float((v.detach() - out[:n_grad]).abs().max())
+
     chains = K * (1 + P)
-    rows = chains * n * (1 + 2 * 25)
-    M, d = cfg["M"], cfg["d"]
-    flop = chains * n * ((2 * M * M + 2 * M + 3 * d * M) + 50 * (2 * M * M + 2 * M + 3 * (d + 1) * M))
-    return {"metric": "jesmoc_acq_evals_per_s", "value": world * n / (ms * 1e-3),
-            "unit": "candidates/s through the full coupled acquisition (6 black boxes x (1 + 16) MFDGPs, S=25, "
-                    "fidelity 2, forward)",
-            "candidates_per_gpu": n, "n_gpus": world, "ms_per_sweep": ms, "model_chains_per_candidate": chains,
-            "model_chain_evals_per_s": world * n * chains / (ms * 1e-3), "rows_per_s": world * rows / (ms * 1e-3),
-            "tflops_per_gpu": flop / (ms * 1e-3) / 1e12, "acq_mean": float(out.mean())}
+    flop = acq_flop_per_candidate(cfg, K, P)
+    tf = n * flop / (ms * 1e-3) / 1e12
+    res = {"metric": "jesmoc_acq_evals_per_s", "value": world * n / (ms * 1e-3),
+           "unit": "candidates/s through the full coupled acquisition (6 black boxes x (1 + 16) MFDGPs, S=25, "
+                   "fidelity 2, forward)",
+           "workload": "C5: %d candidates per GPU x 16 Pareto samples x (4 objectives + 2 constraints), d=6, L=3, "
+                       "M=256, S=25 (10^6 candidates on 8 GPUs)" % n,
+           "candidates_per_gpu": n, "candidates_total": world * n, "n_gpus": world, "ms_per_sweep": ms,
+           "scaling": "weak", "model_chains_per_candidate": chains,
+           "model_chain_evals_per_s": world * n * chains / (ms * 1e-3),
+           "rows_per_s": world * n * chains * 51 / (ms * 1e-3), "acq_mean": float(out.mean()),
+           "roofline": {"bound": "tensor", "kernel": "row_fwd_kernel (eval branch)", "achieved": tf,
+                        "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS, "traffic": None,
+                        "algorithmic_flop_per_candidate": flop, "per_gpu": True,
+                        "peak_source": "measured DMMA fp64 pipe peak, profiles/r01_fp64_probe.log"},
+           "e2e": {"value": world * n / (ms_e2e * 1e-3), "unit": "candidates/s", "h2d_bytes_per_step": n * cfg["d"] * 8,
+                   "d2h_bytes_per_step": n * 8, "ms_per_sweep": ms_e2e, "values_equal_device_run": same,
+                   "note": "pinned host candidates -> H2D -> jes_sweep (102 chains) -> values D2H -> host sync"},
+           "fwd_plus_dX": {"value": world * n_grad / (ms_g * 1e-3), "unit": "candidates/s (forward + d acq / dX)",
+                           "candidates_per_gpu": n_grad, "ms": ms_g, "grad_finite_nonzero": grad_ok,
+                           "max_abs_diff_vs_forward_only": fwd_vs_grad,
+                           "note": "_JES-style autograd through the composable kernels (mobo_layer_rows_fwd/_bwd), "
+                                   "the call optimize_acqf makes (acquisition_functions/JESMOC_MFDGP.py:142-143)"}}
+    if with_cpu and world == 1 and rank == 0:
+        res["cpu_baseline"] = acq_cpu_baseline(boxes, cfg, Xh, out, fidelity, K, P)
+    return res
+
+
+def acq_cpu_baseline(boxes, cfg, Xh, gpu_vals, fidelity, K, P, budget_s=20.0, chunk=200):
+    """the oracle's coupled acquisition on a bounded slice of the SAME candidates in chunks of 200
+    (= raw_samples of optimize_acqf), diagonal-only predictive variance, all host threads; plus ONE literal R x R
+    eval-branch timing (what upstream's eval mode materialises) at the C3 grid size, 625 points x 25 samples."""
+    from oracle import mfdgp_oracle as O
+    from tests.helpers import oracle_view, random_state
+    torch.set_num_threads(os.cpu_count() or 1)
+    L = cfg["L"]
+    mods = []
+    for u, conds in boxes:
+        vu = oracle_view(u)
+        mods.append((vu, [oracle_view(c) for c in conds]))
+    done, t_start, worst = 0, time.time(), 0.0
+    with torch.no_grad():
+        while done < Xh.shape[0]:
+            Xc = Xh[done:done + chunk].clone()
+            acc = torch.zeros(Xc.shape[0], dtype=torch.float64)
+            for (sd, lo, up, smp), conds in mods:
+                _, vu = O.predict_for_acquisition(sd, L, up, smp, Xc, fidelity, noise_lower=lo)
+                for (sdc, loc, upc, smpc) in conds:
+                    _, vc = O.predict_for_acquisition(sdc, L, upc, smpc, Xc, fidelity, noise_lower=loc)
+                    acc += O.jes(vu, vc)
+            acc /= P
+            worst = max(worst, float((acc - gpu_vals[done:done + chunk].cpu()).abs().max()))
+            done += Xc.shape[0]
+            if time.time() - t_start > budget_s:
+                break
+    t = time.time() - t_start
+    out = {"value": done / t, "unit": "candidates/s", "cores": torch.get_num_threads(), "kind": "port",
+           "sample": "oracle coupled acquisition (102 chains, diagonal variance) on the first %d of the candidates in "
+                     "chunks of %d: %.1f s" % (done, chunk, t),
+           "max_abs_diff_vs_gpu": worst}
+    try:    # literal R x R eval branch at the C3 size (d=2, L=2, M=15, 625 grid points x 25 samples = 15 625 rows)
+        sd, up = random_state(15, 2, 2, seed=0, ls=0.3)
+        g = torch.Generator().manual_seed(0)
+        xt = torch.rand(625, 2, generator=g, dtype=torch.float64).repeat_interleave(25, 0)
+        smp = torch.randn(25, generator=g).double()
+        t0 = time.time()
+        with torch.no_grad():
+            m0, v0 = O.layer_q(sd, 0, xt, training=False, literal_eval_cov=True)
+            f = (m0 + torch.sqrt(O.read_variance(v0)) * smp.repeat(625)).reshape(-1, 1)
+            O.layer_q(sd, 1, torch.cat([xt, f], 1), training=False, literal_eval_cov=True)
+        out["literal_RxR_eval_branch_C3"] = {"seconds_per_model_chain": time.time() - t0, "rows": 15625,
+                                             "note": "upstream eval mode builds the R x R predictive covariance and "
+                                                     "reads its diagonal; 2 layers, M = 15"}
+    except (MemoryError, RuntimeError) as e:
+        out["literal_RxR_eval_branch_C3"] = {"error": str(e)[:120]}
+    return out
 
 
 def bench_pareto(dev, d=6, L=3, F=500, K=6, iters=5, with_cpu=True):
@@ -599,10 +728,10 @@ def bench_pareto(dev, d=6, L=3, F=500, K=6, iters=5, with_cpu=True):
     return out
 
 
-def cpu_baseline(cfg, x, y, fid, model, max_seconds=30.0, steps=3, warmup=1):
-    """The oracle's tiled S-sample ELBO step (forward + autograd backward + Adam) on the host cores, on a bounded
-    sample of the same workload: same model / B / M, S reduced to S_cpu and scaled by rows.  This leg (and
-    ``--impl reference``) is the only place where bench.py executes ``oracle/``."""
+def cpu_baseline(cfg, x, y, fid, model, steps=8, warmup=2):
+    """The oracle's tiled S-sample ELBO step (forward + autograd backward + Adam) on the host cores at the FULL C4
+    configuration (B = 1024, M = 256, S = 64, L = 3), every step measured, nothing extrapolated.  This leg (and
+    ``--impl reference``) is the only place where bench.py TIMES ``oracle/``."""
     from oracle import mfdgp_oracle as O
     from tests.helpers import oracle_view
     torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
@@ -610,36 +739,70 @@ def cpu_baseline(cfg, x, y, fid, model, max_seconds=30.0, steps=3, warmup=1):
     names = [n for n, p in model.named_parameters() if p.requires_grad]
     for n in names:
         sd[n].requires_grad_(True)
-    B, S_cpu, N, L = cfg["B"], 8, cfg["N"], cfg["L"]
+    B, S, N, L = cfg["B"], cfg["S"], cfg["N"], cfg["L"]
     g = torch.Generator().manual_seed(5)
     opt = torch.optim.Adam([sd[n] for n in names], lr=0.001)
     times = []
-    t_start = time.time()
     for it in range(warmup + steps):
         idx = torch.randint(0, N, (B,), generator=g)
-        eps = [None] + [torch.randn(B * S_cpu, generator=g).double() for _ in range(1, L)]
+        eps = [None] + [torch.randn(B * S, generator=g).double() for _ in range(1, L)]
         t0 = time.time()
         opt.zero_grad()
-        loss, _ = O.elbo_step_loss_tiled(sd, L, up, x[idx], y[idx], fid[idx], eps, N, S_cpu, noise_lower=lo)
+        loss, _ = O.elbo_step_loss_tiled(sd, L, up, x[idx], y[idx], fid[idx], eps, N, S, noise_lower=lo)
         loss.backward()
         opt.step()
         if it >= warmup:
             times.append(time.time() - t0)
-        if time.time() - t_start > max_seconds and times:
-            break
     t = sum(times) / len(times)
-    rows_full = B + (L - 1) * B * cfg["S"]
-    rows_cpu = B + (L - 1) * B * S_cpu
-    t_full = t * rows_full / rows_cpu
-    return {"value": 1.0 / t_full, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "oracle tiled ELBO step (fwd + autograd bwd + Adam), B=1024, M=256, S=%d of the 64 samples "
-                      "(mean %.3f s over %d steps), scaled by rows x%.2f" % (S_cpu, t, len(times), rows_full / rows_cpu)}
+    return {"value": 1.0 / t, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "seconds_timed": sum(times), "steps_timed": len(times),
+            "sample": "oracle tiled ELBO step (fwd + autograd bwd + torch Adam) at the full C4 step, B=1024, M=256, "
+                      "S=64: mean %.3f s over %d steps after %d warm-up steps, nothing scaled" % (t, len(times), warmup)}
+
+
+def parity_block(cfg, x, y, fid, model, fstep, dev):
+    """CUDA vs CPU oracle on ONE C4 step (same parameters, minibatch and normals), outside the timed region: relative
+    errors of the loss, the KL term and the worst gradient, with cond(K_zz + jitter I) and the bar they are held to
+    (1e-10 on well-conditioned inputs, 20 * eps * cond otherwise; gradients 1e3 x that: SURVEY.md section 7)."""
+    from oracle import mfdgp_oracle as O
+    from tests.helpers import oracle_view, parity_tol, relerr
+    torch.set_num_threads(os.cpu_count() or 1)
+    B, S, N, L = cfg["B"], cfg["S"], cfg["N"], cfg["L"]
+    g = torch.Generator().manual_seed(31)
+    idx = torch.randint(0, N, (B,), generator=g)
+    eps = [None] + [torch.randn(B * S, generator=g).double() for _ in range(1, L)]
+    loss, kl = fstep(x[idx].to(dev), y[idx].to(dev), fid[idx].to(dev),
+                     eps=[None if e is None else e.to(dev) for e in eps], num_samples=S)
+    fstep.check()
+    loss, kl = loss.clone(), kl.clone()
+    grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.requires_grad}
+    sd, lo, up, _ = oracle_view(model)
+    for n in grads:
+        sd[n].requires_grad_(True)
+    t0 = time.time()
+    loss_o, kl_o = O.elbo_step_loss_tiled(sd, L, up, x[idx], y[idx], fid[idx], eps, N, S, noise_lower=lo)
+    loss_o.backward()
+    t_oracle = time.time() - t0
+    worst, where = 0.0, None
+    for n, gc in grads.items():
+        go = sd[n].grad
+        if "chol_variational_covar" in n:
+            gc, go = torch.tril(gc), torch.tril(go)
+        e = relerr(gc, go)
+        if e > worst:
+            worst, where = e, n
+    tol, cond = parity_tol(model)
+    return {"loss_relerr": relerr(loss, loss_o), "kl_relerr": relerr(kl, kl_o), "max_grad_relerr": worst,
+            "max_grad_relerr_param": where, "cond": cond, "tol_values": tol, "tol_grads": 1e3 * tol,
+            "ok": bool(relerr(loss, loss_o) < tol and relerr(kl, kl_o) < tol and worst < 1e3 * tol),
+            "oracle_seconds": t_oracle, "retries": fstep.retries(),
+            "what": "one C4 step (B=1024 x S=64, all parameters trainable) vs oracle/mfdgp_oracle.py on the host"}
 
 
 def run_reference(args):
     """Reference arm: the reference's CPU implementation of the path.  GPyTorch/BoTorch are not installable here
-    (SURVEY.md §8c), so this times the oracle port with all host threads on the same config, each step a bounded
-    sample (S=8 of 64 samples, scaled by rows)."""
+    (SURVEY.md §8c), so this times the oracle port with all host threads on the SAME configuration: every one of the
+    K steps is a full C4 step (B = 1024 x S = 64), W warm-up steps before them."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -649,13 +812,15 @@ def run_reference(args):
     torch.manual_seed(cfg["seed"])
     model = MFDGP(x, y, fid, cfg["L"], num_inducing=cfg["M"], init_lengthscale=cfg["lengthscale"])
     model.double()
-    cb = cpu_baseline(cfg, x, y, fid, model, max_seconds=150.0, steps=max(1, args.steps), warmup=max(1, args.warmup))
+    model.fix_variational_hypers(False)
+    cb = cpu_baseline(cfg, x, y, fid, model, steps=max(1, args.steps), warmup=max(1, args.warmup))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     out = {"impl": "reference", "metric": "mfdgp_elbo_steps_per_s", "value": cb["value"], "unit": "steps/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "C4 scaled MFDGP training: d=6, 3 fidelities, N=50000, M=256, B=1024 rows x S=64 "
-                                  "MC samples (CPU oracle port; GPyTorch not installable)"},
+           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(world, args.scaling, cfg["B"]),
+           "reference_note": "CPU oracle port of the reference path (GPyTorch is not installable here); one process, "
+                             "one 1024 x 64 step unit at a time whatever --gpus says",
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -669,8 +834,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="fused", choices=["fused", "composable"],
                     help="fused: mobo_elbo_step + mobo_adam (product hot loop); composable: autograd over the same kernels")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-acq", action="store_true", help="skip the acquisition slice")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: one 1024 x 64 step unit per GPU; strong: one 1024 x 64 step split over the GPUs")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-acq", action="store_true", help="skip the acquisition sweep and the small-config legs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the CUDA-vs-oracle parity block")
+    ap.add_argument("--acq-candidates", type=int, default=C5_CANDIDATES_PER_GPU,
+                    help="candidates per GPU of the C5 acquisition sweep (10^6 / 8 by default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -143,3 +143,55 @@ class JESMOC_MFDGP():
         if self.eval_highest_fidelity:
             return self._get_nextpoint_coupled_highest_fidelity(iteration=iteration, verbose=verbose)
         return self._get_nextpoint_coupled(iteration=iteration, verbose=verbose)
+
+
+def jes_sweep(X: Tensor, fidelity: int, blackboxes, chunk: int = 1 << 17) -> Tensor:
+    """Coupled JES acquisition averaged over P Pareto-set samples (BASELINE.json configs[4]; the reference conditions on
+    ONE sample, acquisition_functions/JESMOC_MFDGP.py:73-77, so P > 1 is the average of P single-sample acquisitions,
+    SURVEY.md fact F5):
+
+        acq(x) = 1/P sum_p sum_k 1/2 max(0, log v_u,k(x) - log v_c,k,p(x))
+
+    ``blackboxes``: one ``(uncond MFDGP, [cond MFDGP of Pareto sample p, ...])`` pair per objective / constraint.
+    X: (n, d) or (n, 1, d) fp64 CUDA.  Without gradients every model chain is ONE enqueue of the fused acquisition
+    kernels (``mobo_acq_moments`` + ``mobo_jes``), candidates in chunks that bound the n * S scratch; with
+    ``X.requires_grad`` the composable autograd path provides d acq / dX (what optimize_acqf consumes).
+    Candidates are independent: shard X across GPUs with ``util.distributed.shard_bounds``, no collective."""
+    from .. import _lib
+    if X.dim() > 2:
+        assert X.shape[1] == 1
+        X = X[:, 0, :]
+    n = X.shape[0]
+    P = len(blackboxes[0][1])
+    want_grad = torch.is_grad_enabled() and X.requires_grad
+    if want_grad:
+        total = torch.zeros(n, dtype=torch.float64, device=X.device)
+        for unc, conds in blackboxes:
+            unc.eval()
+            _, vu = unc.predict_for_acquisition(X, fidelity)
+            unc.train()
+            lvu = torch.log(vu)
+            for c in conds:
+                c.eval()
+                _, vc = c.predict_for_acquisition(X, fidelity)
+                c.train()
+                total = total + 0.5 * torch.clamp(lvu - torch.log(vc), min=0.0)
+        return total / P
+    lib = _lib.load()
+    out = torch.zeros(n, dtype=torch.float64, device=X.device)
+    with torch.no_grad():
+        for a in range(0, n, chunk):
+            xa = X[a:a + chunk].contiguous()
+            oa = out[a:a + chunk]
+            for unc, conds in blackboxes:
+                unc.eval()
+                _, vu = unc.predict_for_acquisition(xa, fidelity)
+                unc.train()
+                for c in conds:
+                    c.eval()
+                    _, vc = c.predict_for_acquisition(xa, fidelity)
+                    c.train()
+                    _lib.check(lib.mobo_jes(_lib.ptr(vu), _lib.ptr(vc), xa.shape[0], 1, _lib.ptr(oa),
+                                            _lib.stream_ptr()), "mobo_jes")
+        out.div_(P)
+    return out

@@ -115,7 +115,7 @@ class MFDGP(nn.Module):
         raise ValueError("Wrong type of lengthscale.")
 
     @staticmethod
-    def median_lengthscale(inputs, literal=False):
+    def median_lengthscale(inputs, literal=False, use_cuda=None):
         """``sqrt(median(dists[triu_indices(n, 1)]))`` of models/mfdgp.py:143-144 INCLUDING quirk Q2: the (2, K)
         LongTensor indexes ROWS of the distance matrix (util/util.py:27-30), so the reference takes the median of a
         (2, K, n) gather, n^2 (n - 1) values — unusable beyond a few hundred points.  Every row of the matrix occurs
@@ -127,7 +127,9 @@ class MFDGP(nn.Module):
             dists_x_train = compute_dist(inputs)
             return torch.sqrt(torch.median(dists_x_train[triu_indices(n, 1)]))
         x = inputs
-        if not x.is_cuda and torch.cuda.is_available() and n > 2048:
+        if use_cuda is None:
+            use_cuda = torch.cuda.is_available() and n > 2048
+        if use_cuda and not x.is_cuda:
             x = x.cuda()
         flat = compute_dist(x).reshape(-1)
         k = ((n * n * (n - 1) - 1) // 2) // (n - 1)

@@ -94,8 +94,11 @@ class _GraphedConditionedStep(object):
     buffers, x-tilde and the training normals are drawn inside the graph by torch's graph-safe generator.  An
     iteration whose minibatch equals the inducing inputs (quirk Q4 changes the arithmetic) runs eagerly."""
 
-    def __init__(self, fitter, handlers_objs, handlers_cons, optimizer, warmup=2):
+    def __init__(self, fitter, handlers_objs, handlers_cons, optimizer, warmup=2, static_noise=False):
         self.fitter, self.optimizer, self.warmup = fitter, optimizer, warmup
+        # static_noise (parity tests): x-tilde and the training normals are staged by the caller on every call instead
+        # of being drawn inside the graph, so that a replay can be compared with the eager iteration
+        self.static_noise = static_noise
         self.hs_o, self.hs_c = list(handlers_objs), list(handlers_cons)
         self.keys = [("obj", i) for i in range(len(self.hs_o))] + [("con", k) for k in range(len(self.hs_c))]
         self.handlers = self.hs_o + self.hs_c
@@ -138,9 +141,11 @@ class _GraphedConditionedStep(object):
                 return True
         return False
 
-    def _iteration(self, static):
-        self.x_tilde.uniform_()
-        loss = self.fitter.conditioned_loss(self.hs_o, self.hs_c, x_tilde=self.x_tilde, batches=static)
+    def _iteration(self, static, static_eps=None):
+        if not self.static_noise:
+            self.x_tilde.uniform_()
+        loss = self.fitter.conditioned_loss(self.hs_o, self.hs_c, x_tilde=self.x_tilde, batches=static,
+                                            eps=static_eps)
         loss.backward()
         self.optimizer.step()
         return loss.detach()
@@ -151,44 +156,57 @@ class _GraphedConditionedStep(object):
             for i in range(m.num_hidden_layers):
                 yield getattr(m, m.name_hidden_layer + str(i))
 
-    def _capture(self, batches):
+    def _capture(self, batches, eps=None):
         static = {}
         for key in self.keys:
             bufs = tuple(t.detach().clone() for t in batches[key])
             bufs[0]._mobo_not_z = True          # checked on the host for every minibatch (_hits_shortcut)
             static[key] = bufs
+        static_eps = None
+        if self.static_noise:
+            static_eps = {key: {w: [None if e is None else e.detach().clone() for e in lst]
+                                for w, lst in eps[key].items()} for key in self.keys}
         snap = self.optimizer.snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(self.warmup):
                 self.optimizer.zero_grad(set_to_none=True)
-                self._iteration(static)
+                self._iteration(static, static_eps)
         torch.cuda.current_stream().wait_stream(side)
         self.optimizer.zero_grad(set_to_none=True)
         for layer in self._layers():
             layer._ops_cache = None
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            loss = self._iteration(static)
+            loss = self._iteration(static, static_eps)
         self.optimizer.restore(snap)    # warm-up and capture do not count as training iterations
-        return static, graph, loss
+        return static, graph, loss, static_eps
 
-    def __call__(self):
-        batches = self._fetch()
+    def __call__(self, batches=None, x_tilde=None, eps=None):
+        if batches is None:
+            batches = self._fetch()
+        if self.static_noise:
+            self.x_tilde.copy_(x_tilde)
         if not self.capturable or self._hits_shortcut(batches):
             self.optimizer.zero_grad()
-            loss = self.fitter.conditioned_loss(self.hs_o, self.hs_c, batches=batches)
+            loss = self.fitter.conditioned_loss(self.hs_o, self.hs_c, batches=batches, eps=eps,
+                                                x_tilde=self.x_tilde if self.static_noise else None)
             loss.backward()
             self.optimizer.step()
             return loss.detach()
         shape_key = tuple(tuple(t.shape) for key in self.keys for t in batches[key])
         if shape_key not in self.graphs:
-            self.graphs[shape_key] = self._capture(batches)
-        static, graph, loss = self.graphs[shape_key]
+            self.graphs[shape_key] = self._capture(batches, eps)
+        static, graph, loss, static_eps = self.graphs[shape_key]
         for key in self.keys:
             for dst, src in zip(static[key], batches[key]):
                 dst.copy_(src)
+            if static_eps is not None:
+                for w, lst in static_eps[key].items():
+                    for dst, src in zip(lst, eps[key][w]):
+                        if dst is not None:
+                            dst.copy_(src)
         graph.replay()
         for layer in self._layers():
             layer._ops_cache = None       # the cached operators belong to the graph's memory pool

@@ -89,15 +89,21 @@ def variational_q(sd, l):
 
 
 def layer_inducing_points(sd, l):
-    """Z_l = [Z, m_{l-1}] (shared inducing inputs: quirk Q4 makes the previous layer return its mean exactly)."""
+    """Z_l = [Z[:, :d], previous_layer(Z[:, :d]).mean] (layers/mfdgp_hidden_layer.py:542-559).  With shared inducing
+    inputs quirk Q4 makes the previous layer return its variational mean exactly; otherwise (only-highest-fidelity
+    models keep per-layer inducing inputs) layer 0 is evaluated at them."""
     Zo = sd[_key_layer(l) + "variational_strategy.inducing_points"]
     if l == 0:
         return Zo
     d = Zo.shape[1] - 1
     zx = Zo[:, :d]
     zprev = sd[_key_layer(l - 1) + "variational_strategy.inducing_points"]
-    assert np.array_equal(zx.v, zprev.v[:, :d]), "the truth assumes shared inducing inputs"
-    return A.cat([zx, A.reshape(variational_q(sd, l - 1)[0], (-1, 1))], axis=1)
+    if zprev.v.shape[0] == zx.v.shape[0] and np.array_equal(zx.v, zprev.v[:, :d]):
+        mean_prev = variational_q(sd, l - 1)[0]
+    else:
+        assert l == 1, "non-shared inducing inputs above layer 1 crash in the reference too (F3)"
+        mean_prev, _ = layer_q(sd, 0, zx, True)
+    return A.cat([zx, A.reshape(mean_prev, (-1, 1))], axis=1)
 
 
 def prior_cholesky(sd, l, Z, jitter=JITTER):
@@ -148,7 +154,7 @@ def expected_log_prob(target, mean, var, noise):
 
 
 def elbo_step_loss_tiled(sd, L, noise_upper, x, y, fid, eps, num_data, S, noise_lower=NOISE_LOWER, jitter=JITTER,
-                         x_node=None):
+                         x_node=None, only_hf=False):
     """-ELBO of the S-sample tiled step (the oracle's ``elbo_step_loss_tiled``; S = 1 with (1, B) normals is the
     reference's own step).  x, y, fid, eps: torch tensors / arrays (constants); returns (loss node, kl node)."""
     X = A.const(x) if x_node is None else x_node
@@ -160,8 +166,12 @@ def elbo_step_loss_tiled(sd, L, noise_upper, x, y, fid, eps, num_data, S, noise_
     x_tile = A.repeat_interleave(X, S, 0)
     pm, pv = A.repeat_interleave(mean, S, 0), A.repeat_interleave(var, S, 0)
     for l in range(1, L):
-        e = np.asarray(eps[l].detach().cpu().numpy() if hasattr(eps[l], "detach") else eps[l], dtype=LD).reshape(-1)
-        f = A.reshape(e * A.sqrt(read_variance(pv)) + pm, (-1, 1))
+        if only_hf:                                      # models/mfdgp.py:189-190: the passed mean is zeroed
+            f = A.reshape(pm * 0.0, (-1, 1))
+        else:
+            e = np.asarray(eps[l].detach().cpu().numpy() if hasattr(eps[l], "detach") else eps[l],
+                           dtype=LD).reshape(-1)
+            f = A.reshape(e * A.sqrt(read_variance(pv)) + pm, (-1, 1))
         pm, pv = layer_q(sd, l, A.cat([x_tile, f], axis=1), True, jitter)
         outs.append((pm, pv))
     data = A.const(0.0)
@@ -209,10 +219,12 @@ def jes(vu, vc):
 
 
 # ---- convenience drivers used by the tests --------------------------------------------------------------------
-def elbo_step_truth(sd_torch, names, L, noise_upper, x, y, fid, eps, num_data, S, noise_lower=NOISE_LOWER):
+def elbo_step_truth(sd_torch, names, L, noise_upper, x, y, fid, eps, num_data, S, noise_lower=NOISE_LOWER,
+                    only_hf=False):
     """(loss, kl, {name: gradient}) as longdouble arrays."""
     sd = leaves(sd_torch, set(names))
-    loss, kl = elbo_step_loss_tiled(sd, L, noise_upper, x, y, fid, eps, num_data, S, noise_lower=noise_lower)
+    loss, kl = elbo_step_loss_tiled(sd, L, noise_upper, x, y, fid, eps, num_data, S, noise_lower=noise_lower,
+                                    only_hf=only_hf)
     A.backward(loss)
     grads = {n: (sd[n].g if sd[n].g is not None else np.zeros(sd[n].v.shape, dtype=LD)) for n in names}
     return loss.v, kl.v, grads

@@ -152,3 +152,53 @@ def model_from_state(sd, noise_upper, L, samples=None, device="cuda:0", noise_lo
                 layer.num_samples_for_acquisition = samples[l].shape[0]
                 model.num_samples_for_acquisition = samples[l].shape[0]
     return model.to(device)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# extended-precision adjudication (oracle/mfdgp_truth.py): the bar for ill-conditioned cases
+# ------------------------------------------------------------------------------------------------------------
+ADJ_C = 10.0        # the CUDA path may be at most this many times further from the exact answer than the fp64 oracle
+ADJ_FLOOR = 1e-10   # ... or within the north-star tolerance of it, whichever is larger
+
+
+def adjudicate(tag, cuda, oracle, truth, c=ADJ_C, floor=ADJ_FLOOR, report=None):
+    """Asserts |cuda - truth| <= max(floor, c * |oracle - truth|) (max-norm, relative to max |truth|).  ``truth`` is a
+    numpy longdouble array from oracle/mfdgp_truth.py, whose own rounding error is ~2000x below fp64's."""
+    from oracle import mfdgp_truth as T
+    ec, eo = T.err_vs(cuda, truth), T.err_vs(oracle, truth)
+    if report is not None:
+        report.append((tag, ec, eo))
+    assert ec <= max(floor, c * eo), "%s: |cuda - truth| = %.2e but |oracle - truth| = %.2e" % (tag, ec, eo)
+    return ec, eo
+
+
+def adjudicate_state(sd, lo, up, loss_cuda, grads_cuda, loss_oracle, grads_oracle, L, xb, yb, fb, eps, num_data, S,
+                     c=ADJ_C, floor=ADJ_FLOOR, verbose=True, only_hf=False):
+    """Loss (= -ELBO) and EVERY gradient of one ELBO step on the oracle-format state ``sd``: CUDA vs fp64 oracle,
+    adjudicated by the longdouble truth evaluated on the same parameters, minibatch and normals.
+    grads_*: {parameter name: tensor}.  Returns [(tag, err_cuda, err_oracle)]."""
+    import numpy as np
+    from oracle import mfdgp_truth as T
+    names = sorted(grads_oracle)
+    sd = {k: v.detach() for k, v in sd.items()}
+    loss_t, _, grads_t = T.elbo_step_truth(sd, names, L, up, xb, yb, fb, eps, num_data, S, noise_lower=lo,
+                                           only_hf=only_hf)
+    rep = []
+    adjudicate("loss", loss_cuda, loss_oracle, loss_t, c, floor, rep)
+    for n in names:
+        gc, go, gt = grads_cuda[n], grads_oracle[n], grads_t[n]
+        if "chol_variational_covar" in n:
+            gc, go, gt = torch.tril(gc), torch.tril(go), np.tril(gt)
+        adjudicate(n, gc, go, gt, c, floor, rep)
+    if verbose:
+        worst = max(rep, key=lambda r: r[1])
+        print("adjudicated %d quantities: worst |cuda - truth| %.2e (%s), there |oracle - truth| %.2e; "
+              "max |oracle - truth| %.2e" % (len(rep), worst[1], worst[0], worst[2], max(r[2] for r in rep)))
+    return rep
+
+
+def adjudicate_step(model, loss_cuda, grads_cuda, loss_oracle, grads_oracle, L, xb, yb, fb, eps, num_data, S, **kw):
+    """``adjudicate_state`` on a product model's parameters."""
+    sd, lo, up, _ = oracle_view(model)
+    return adjudicate_state(sd, lo, up, loss_cuda, grads_cuda, loss_oracle, grads_oracle, L, xb, yb, fb, eps,
+                            num_data, S, **kw)

@@ -1,0 +1,103 @@
+"""GPU parity AT THE BENCHMARKED OPERATING POINT (BASELINE.json configs[3], SURVEY.md section 8d "C4"): d = 6, L = 3,
+N = 50 000, M = 256, minibatch B = 1024 x S = 64 MC samples, fp64 - the exact model and data bench.py times - in both
+hyper-parameter settings of section 8d: well-conditioned (lengthscale 0.3: the 1e-10 claim) and the reference's default
+TL.MEDIAN initialisation (cond ~ 1e7 - 1e8: error reported against cond * eps, gradients adjudicated by the
+longdouble truth on a row subset of the same model)."""
+import pytest
+import torch
+
+from oracle import mfdgp_oracle as O
+from tests.helpers import adjudicate_step, oracle_view, parity_tol, relerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _c4(lengthscale):
+    import bench
+    cfg = dict(bench.C4)
+    cfg["lengthscale"] = lengthscale
+    x, y, fid = bench.c4_data(cfg)
+    model = bench.build_model(cfg, x, y, fid, torch.device(DEV))
+    model.fix_variational_hypers(False)
+    return cfg, x, y, fid, model
+
+
+def _step_and_oracle(cfg, x, y, fid, model, B, S, seed=0):
+    from mobocmf_b200.fused import FusedELBOStep
+    from mobocmf_b200.mlls.variational_elbo_mf import VariationalELBOMF
+    L, N = cfg["L"], cfg["N"]
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randint(0, N, (B,), generator=g)
+    eps = [None] + [torch.randn(B * S, generator=g).double() for _ in range(1, L)]
+    step = FusedELBOStep(model, VariationalELBOMF(model, N, L))
+    loss, kl = step(x[idx].to(DEV), y[idx].to(DEV), fid[idx].to(DEV),
+                    eps=[None if e is None else e.to(DEV) for e in eps], num_samples=S)
+    step.check()
+    loss, kl = loss.clone(), kl.clone()
+    grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.requires_grad}
+    sd, lo, up, _ = oracle_view(model)
+    for n in grads:
+        sd[n].requires_grad_(True)
+    loss_o, kl_o = O.elbo_step_loss_tiled(sd, L, up, x[idx], y[idx], fid[idx], eps, N, S, noise_lower=lo)
+    loss_o.backward()
+    return (loss, kl, grads), (loss_o.detach(), kl_o.detach(), {n: sd[n].grad for n in grads}), (idx, eps), step
+
+
+def _worst_grad(grads, grads_o):
+    worst, where = 0.0, None
+    for n in grads:
+        a, b = grads[n], grads_o[n]
+        if "chol_variational_covar" in n:
+            a, b = torch.tril(a), torch.tril(b)
+        e = relerr(a, b)
+        if e > worst:
+            worst, where = e, n
+    return worst, where
+
+
+def test_c4_exact_config_well_conditioned():
+    cfg, x, y, fid, model = _c4(0.3)
+    tol, cond = parity_tol(model)
+    (loss, kl, grads), (loss_o, kl_o, grads_o), _, _ = _step_and_oracle(cfg, x, y, fid, model, cfg["B"], cfg["S"])
+    worst, where = _worst_grad(grads, grads_o)
+    print("C4 (l = 0.3): cond %.2e  tol %.1e  loss relerr %.2e  KL relerr %.2e  worst grad relerr %.2e (%s)"
+          % (cond, tol, relerr(loss, loss_o), relerr(kl, kl_o), worst, where))
+    assert cond < 1e5
+    assert relerr(loss, loss_o) < tol and relerr(kl, kl_o) < tol
+    assert worst < 1e3 * tol, (where, worst)
+
+
+def test_c4_exact_config_reference_default_lengthscale():
+    """TL.MEDIAN at N = 50 000 (30 000 / 15 000 / 5 000 points per fidelity): also the only caller of the
+    n > 2048 device branch of the median heuristic (models/mfdgp.py:143-144, quirk Q2)."""
+    cfg, x, y, fid, model = _c4(None)
+    ls0 = float(model.hidden_layer_0.covar_module.base_kernel.lengthscale.reshape(-1)[0])
+    assert 0.8 < ls0 < 1.2, ls0                    # sqrt(median squared distance) on U[0,1]^6 ~ 0.98
+    tol, cond = parity_tol(model)
+    assert cond > 1e6
+    (loss, kl, grads), (loss_o, kl_o, grads_o), _, step = _step_and_oracle(cfg, x, y, fid, model, cfg["B"], cfg["S"])
+    worst, where = _worst_grad(grads, grads_o)
+    print("C4 (TL.MEDIAN, l0 = %.3f): cond %.2e  cond*eps bar %.1e  loss relerr %.2e  KL relerr %.2e  worst grad "
+          "relerr vs fp64 oracle %.2e (%s)  retries %d" % (ls0, cond, tol, relerr(loss, loss_o), relerr(kl, kl_o),
+                                                           worst, where, step.retries()))
+    assert relerr(loss, loss_o) < tol and relerr(kl, kl_o) < tol
+    # gradients: the same model on a row subset that the longdouble truth can afford (conditioning is a property of
+    # the M x M operators, not of the row count): |cuda - truth| <= 10 |oracle - truth| for the loss and every gradient
+    B2, S2 = 96, 4
+    (loss2, _, grads2), (loss2_o, _, grads2_o), (idx, eps), _ = _step_and_oracle(cfg, x, y, fid, model, B2, S2, seed=1)
+    rep = adjudicate_step(model, loss2, grads2, loss2_o, grads2_o, cfg["L"], x[idx], y[idx], fid[idx], eps, cfg["N"], S2)
+    # full size: the disagreement with the fp64 oracle stays within the two sides' adjudicated error levels
+    level = max(max(r[1], r[2]) for r in rep)
+    assert worst < max(1e3 * 1e-10, 100 * level), (where, worst, level)
+
+
+def test_median_lengthscale_device_branch_matches_host():
+    from mobocmf_b200.models.mfdgp import MFDGP
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2500, 6, generator=g, dtype=torch.float64)
+    host = MFDGP.median_lengthscale(x, use_cuda=False)
+    dev = MFDGP.median_lengthscale(x, use_cuda=True)
+    assert dev.device == x.device and abs(float(dev) - float(host)) < 1e-13 * float(host)
+    small = torch.rand(40, 3, generator=g, dtype=torch.float64)
+    assert float(MFDGP.median_lengthscale(small)) == float(MFDGP.median_lengthscale(small, literal=True))

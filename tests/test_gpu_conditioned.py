@@ -108,8 +108,66 @@ def test_graph_captured_conditioned_training_runs_and_learns():
             assert all(bool(torch.isfinite(p).all()) for p in hh.mfdgp.parameters())
         assert noise_before == [float(h.mfdgp.hidden_layer_likelihood_1.noise_covar.raw_noise) for h in hs[0]]
         if use_graph:
-            assert cond._cond_graphs and next(iter(cond._cond_graphs.values())).graph is not None
+            assert cond._cond_graphs and next(iter(cond._cond_graphs.values())).graphs
         finals[use_graph] = (first, last)
     # the two loops start from the same point and optimise the same stochastic objective
     assert abs(finals[True][0] - finals[False][0]) < 1e-3 * abs(finals[False][0])   # same data, seeds; other RNG use
     assert abs(finals[True][1] - finals[False][1]) < 0.2 * abs(finals[False][0] - finals[False][1]) + 1.0
+
+
+def test_graph_captured_conditioned_iteration_equals_eager():
+    """The CUDA-graph replay of the conditioned iteration computes exactly what the eager iteration does (loss and, after
+    several iterations, every parameter to 1e-12) when both get the same minibatches, x-tilde and training normals.
+    The eager iteration is the one checked against the oracle above (which keeps torch.prod and ell[mask]); the captured
+    one adds stream forks, static buffers and the device-resident Adam step count."""
+    import copy
+    from mobocmf_b200.fused import Adam
+    from mobocmf_b200.util.blackbox_mfdgp_fitter import BlackBoxMFDGPFitter, _GraphedConditionedStep
+    x, ys, fid = forrester_data()
+    N, L, P, T = x.shape[0], 2, 7, 10
+    torch.manual_seed(0)
+    fitter = BlackBoxMFDGPFitter(L, N, num_epochs_1=0, num_epochs_2=0, device=torch.device(DEV))
+    fitter.verbose = False
+    fitter.initialize_mfdgp(x, ys["obj1"], fid, "obj1")
+    fitter.initialize_mfdgp(x, ys["obj2"], fid, "obj2")
+    fitter.initialize_mfdgp(x, ys["con1"], fid, "con1", threshold_constraint=0.1, is_constraint=True)
+    g = torch.Generator().manual_seed(3)
+    fitter.pareto_set = torch.rand(P, 1, generator=g, dtype=torch.float64).to(DEV)
+    fitter.pareto_front = torch.randn(P, 2, generator=g, dtype=torch.float64).to(DEV)
+    twin = copy.deepcopy(fitter)
+    runs = {}
+    for name, ft in (("eager", fitter), ("graph", twin)):
+        hobjs, hcons = list(ft.mfdgp_handlers_objs.values()), list(ft.mfdgp_handlers_cons.values())
+        params = []
+        for h in hobjs + hcons:
+            h.mfdgp.fix_variational_hypers_cond(True)
+            params += list(h.mfdgp.parameters())
+        opt = Adam([{"params": params}], lr=1e-2, capturable=(name == "graph"))
+        gstep = _GraphedConditionedStep(ft, hobjs, hcons, opt, static_noise=True) if name == "graph" else None
+        gg = torch.Generator().manual_seed(17)
+        keys = [("obj", 0), ("obj", 1), ("con", 0)]
+        losses = []
+        for it in range(5):
+            batches, eps = {}, {}
+            for key, h in zip(keys, hobjs + hcons):
+                perm = torch.randperm(N, generator=gg).to(DEV)
+                batches[key] = (h.x[perm], h.y[perm], h.f[perm])
+                eps[key] = {w: [None, torch.randn(1, n, generator=gg).double().to(DEV)]
+                            for w, n in (("batch", N), ("pareto", P), ("tilde", T))}
+            x_tilde = torch.rand(T, 1, generator=gg, dtype=torch.float64).to(DEV)
+            if gstep is not None:
+                losses.append(float(gstep(batches=batches, x_tilde=x_tilde, eps=eps)))
+            else:
+                opt.zero_grad()
+                loss = ft.conditioned_loss(hobjs, hcons, x_tilde=x_tilde, batches=batches, eps=eps)
+                loss.backward()
+                opt.step()
+                losses.append(float(loss))
+        if gstep is not None:
+            assert gstep.graphs, "the iteration was not captured"
+        runs[name] = (losses, [p.detach().clone() for p in params])
+    for a, b in zip(runs["eager"][0], runs["graph"][0]):
+        assert abs(a - b) <= 1e-12 * abs(a), (a, b)
+    assert runs["eager"][0][-1] != runs["eager"][0][0]
+    for a, b in zip(runs["eager"][1], runs["graph"][1]):
+        assert relerr(b, a) < 1e-12, relerr(b, a)

@@ -43,6 +43,14 @@ def test_ragged_shapes_fused_step(M, d, L, B, S):
     tol = max(1e-10, 20 * 2.2e-16 * cond)
     assert relerr(loss, loss_o) < tol and relerr(kl, kl_o) < tol, (relerr(loss, loss_o), tol)
     grads = {n: p.grad for n, p in model.named_parameters()}
+    if cond >= 1e5:       # ill-conditioned: adjudicated by the longdouble truth (tests/helpers.adjudicate)
+        from tests.helpers import adjudicate_state
+        keys = param_keys(sd)
+        zero = lambda k: torch.zeros_like(sd[k])
+        adjudicate_state(sd, O.NOISE_LOWER, noise_upper, loss, {k: grads[k] for k in keys}, loss_o.detach(),
+                         {k: (sdo[k].grad if sdo[k].grad is not None else zero(k)) for k in keys}, L, x, y, fid, eps,
+                         5 * B, S)
+        return
     for k in param_keys(sd):
         gp, go = grads[k], sdo[k].grad
         if "chol_variational_covar" in k:
@@ -50,7 +58,7 @@ def test_ragged_shapes_fused_step(M, d, L, B, S):
         if go is None or float(go.abs().max()) == 0.0:     # parameter not reached by this minibatch (e.g. one fidelity only)
             assert float(gp.abs().max()) < 1e-12, k
             continue
-        assert relerr(gp.reshape(-1), go.reshape(-1)) < (1e3 * tol if cond < 1e5 else 1e-2), (k, relerr(gp.reshape(-1), go.reshape(-1)))
+        assert relerr(gp.reshape(-1), go.reshape(-1)) < 1e3 * tol, (k, relerr(gp.reshape(-1), go.reshape(-1)))
 
 
 @pytest.mark.parametrize("n", [1, 31, 32, 33, 257])
@@ -116,3 +124,56 @@ def test_not_positive_definite_is_reported():
     step(x, torch.zeros(B, 1, dtype=torch.float64, device=DEV), torch.zeros(B, 1, dtype=torch.float64, device=DEV))
     with pytest.raises(RuntimeError, match="NotPSDError|NanError"):
         step.check()
+
+
+@pytest.mark.parametrize("jitter,retries", [(1e-6, 0), (-5e-9, 1), (-5e-8, 2), (-5e-7, 3)])
+def test_psd_safe_cholesky_retries_on_device(jitter, retries):
+    """Upstream factors K(Z, Z) + jitter I with psd_safe_cholesky: on a non-positive pivot it retries with 1e-8, 1e-7,
+    1e-6 more on the diagonal.  The operator-chain kernel does the same inside the launch.
+    A duplicated inducing input gives K an exactly-zero eigenvalue, so P's smallest eigenvalue IS the jitter: a barely
+    negative one needs exactly 1, 2 or 3 retries.  The factor, the KL and the predictive moments then equal the
+    oracle's, which calls its restatement of psd_safe_cholesky on the same matrix."""
+    from mobocmf_b200 import functional as F
+    M, d = 40, 2
+    sd, noise_upper = random_state(M, d, 1, seed=6, ls=0.4)
+    Zk = "hidden_layer_0.variational_strategy.inducing_points"
+    sd[Zk][7] = sd[Zk][3]
+    Z = sd[Zk]
+    P = O.layer_kernel(sd, 0, Z, Z) + jitter * torch.eye(M, dtype=torch.float64)
+    L_o = O.psd_safe_cholesky(P)
+    if retries:
+        assert bool(torch.linalg.cholesky_ex(P)[1] != 0)                       # the first attempt does fail
+    h = O.layer_hypers(sd, 0)
+    theta = torch.cat([h["a"].reshape(1), h["ls"].reshape(-1)]).to(DEV)
+    m, Lq = O.variational_q(sd, 0)
+    ops = F.layer_operators(theta, None, m.to(DEV), sd["hidden_layer_0.variational_strategy._variational_distribution."
+                                                       "chol_variational_covar"].to(DEV), Z.to(DEV), 0, jitter)
+    lay = F.ops_layout(M)
+    MP = lay["MP"]
+    scal = ops[lay["scal"]:lay["scal"] + 16].cpu()
+    assert scal[F.SC_STATUS] == 0.0 and int(scal[7]) == retries, scal
+    L_c = ops[lay["L"]:lay["L"] + MP * MP].reshape(MP, MP)[:M, :M].cpu()
+    # the smallest eigenvalue is ~5e-8 .. 5e-7 after the rescue: cond ~ 1e9, so the factor agrees to ~cond * eps
+    assert relerr(L_c, L_o) < 1e-6, relerr(L_c, L_o)
+    kl_o = O.kl_layer(sd, 0, jitter)
+    assert abs(float(scal[F.SC_KL]) - float(kl_o)) < 1e-6 * abs(float(kl_o))
+    F.check_status()                                                           # nothing sticky was recorded
+
+
+def test_psd_failure_after_all_retries_is_sticky_in_the_composable_path():
+    from mobocmf_b200 import functional as F
+    from mobocmf_b200.errors import NotPSDError
+    M, d = 16, 2
+    sd, _ = random_state(M, d, 1, seed=6, ls=0.4)
+    Z = sd["hidden_layer_0.variational_strategy.inducing_points"]
+    Z[5] = Z[2]
+    h = O.layer_hypers(sd, 0)
+    theta = torch.cat([h["a"].reshape(1), h["ls"].reshape(-1)]).to(DEV)
+    m, Lq = O.variational_q(sd, 0)
+    F.check_status()
+    ops = F.layer_operators(theta, None, m.to(DEV), Lq.to(DEV), Z.to(DEV), 0, -1e-3)
+    lay = F.ops_layout(M)
+    assert float(ops[lay["scal"] + F.SC_STATUS]) == 1.0 and int(ops[lay["scal"] + 7]) == 3
+    with pytest.raises(NotPSDError):
+        F.check_status()
+    F.check_status()          # cleared by the raise

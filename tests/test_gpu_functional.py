@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import mfdgp_oracle as O
-from tests.helpers import random_state, clone_state, param_keys, relerr
+from tests.helpers import adjudicate_state, random_state, clone_state, param_keys, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -123,5 +123,10 @@ def test_forward_backward_matches_oracle(M, d, R, L, ls):
         e = relerr(gc, go)
         worst = max(worst, e)
         print("grad %-90s relerr %.2e" % (k, e))
-    # gradients go through P^-1 twice: beyond cond ~ 1e5 only a loose agreement is meaningful in fp64
-    assert worst < (100 * tol if max(conds) < 1e5 else 1e-3)
+    if max(conds) < 1e5:
+        assert worst < 100 * tol
+    else:
+        # ill-conditioned: the longdouble truth decides whether the CUDA gradients are as good as the oracle's
+        keys = param_keys(sd)
+        adjudicate_state(sd, O.NOISE_LOWER, noise_upper, -elbo_c.detach(), {k: -sdc[k].grad for k in keys},
+                         -elbo_o.detach(), {k: -sdo[k].grad for k in keys}, L, x, y, fid, eps, num_data, 1)

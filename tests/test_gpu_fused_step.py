@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import mfdgp_oracle as O
-from tests.helpers import synthetic_data, forrester_data, oracle_view, relerr, parity_tol
+from tests.helpers import adjudicate_step, synthetic_data, forrester_data, oracle_view, relerr, parity_tol
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -89,11 +89,32 @@ def test_fused_step_matches_oracle_and_composable(L, S, B, M, freeze):
     loss_o.backward()
     print("cond %.2e tol %.1e loss relerr %.2e" % (cond, tol, relerr(loss, loss_o)))
     assert relerr(loss, loss_o) < tol and relerr(kl, kl_o) < tol
+    rows = B + (L - 1) * B * S
+    if cond >= 1e5 and rows <= 2500:
+        # ill-conditioned: fp64 itself loses digits, so the judge is the longdouble truth, not a wider bar
+        adjudicate_step(model, loss, g_fused, loss_o.detach(), {n: sd[n].grad for n in names}, L, x[idx], y[idx],
+                        fid[idx], eps, N, S)
+        return
+    if cond >= 1e5:
+        # too many rows for the longdouble truth (minutes).  The per-row arithmetic of these kernels IS adjudicated by
+        # the smaller cases above; what this case adds is several tiles per persistent CTA.  That is checked without
+        # any conditioning caveat by additivity: the step's gradients equal the sum over 5 row shards, each small
+        # enough for one tile per CTA (the single-tile path the truth has verified).
+        full = torch.cat([g_fused[n].reshape(-1) for n, p in model.named_parameters() if p.requires_grad])
+        acc = torch.zeros_like(full)
+        nsh = 5
+        for r in range(nsh):
+            a, b = r * B // nsh, (r + 1) * B // nsh
+            e = [None] + [t[a * S:b * S] for t in eps_d[1:]]
+            step(xb[a:b], yb[a:b], fb[a:b], eps=e, num_samples=S)
+            acc += step.flat.flat
+        # every shard carries the KL term scaled by its own B_r / N: they add up to the full step's B / N
+        assert relerr(acc, full) < 1e-10, relerr(acc, full)
     for n in names:
         gf, go = g_fused[n], sd[n].grad
         if "chol_variational_covar" in n:
             gf, go = torch.tril(gf), torch.tril(go)
-        assert relerr(gf, go) < (1e3 * tol if cond < 1e5 else 1e-2), (n, relerr(gf, go))
+        assert relerr(gf, go) < 1e3 * tol, (n, relerr(gf, go))
 
 
 def test_fused_step_single_sample_matches_reference_shaped_oracle():
@@ -257,3 +278,72 @@ def test_cuda_graph_replay_matches_eager_steps():
     for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
         assert relerr(a, b) < 1e-12, (n, relerr(a, b))
     assert int(o1._step_dev) == 6 and len(o1._cohorts) == 1
+
+
+def test_graphed_steps_with_ragged_last_batch_share_one_fused_step():
+    """N % batch_size != 0 with CUDA graphs (the reference's DataLoader yields the short last batch like any other):
+    one FusedELBOStep serves TWO captured graphs (B = 10 and B = 6).  Each graph bakes its workspace address in, so
+    the workspaces must both stay alive; and capturing the second graph mid-training must not disturb the optimiser
+    state accumulated with the first.  Three epochs of alternating replays equal the eager fused loop to 1e-12."""
+    from mobocmf_b200.fused import Adam, FusedELBOStep, GraphedELBOStep
+    from mobocmf_b200.mlls.variational_elbo_mf import VariationalELBOMF
+    L, S = 2, 2
+    m1, x, y, fid, N = make_model(L=L, M=16, n_per=(10, 6), d=2)
+    m2 = copy.deepcopy(m1)
+    e1, e2 = VariationalELBOMF(m1, N, L), VariationalELBOMF(m2, N, L)
+    o1 = Adam([{"params": m1.parameters()}], lr=0.01, capturable=True)
+    o2 = Adam([{"params": m2.parameters()}], lr=0.01)
+    f1, f2 = FusedELBOStep(m1, e1), FusedELBOStep(m2, e2)
+    graphs = {}
+    g = torch.Generator().manual_seed(3)
+    for epoch in range(3):
+        perm = torch.randperm(N, generator=g)
+        for a in (0, 10):
+            idx = perm[a:a + 10]
+            B = idx.numel()
+            eps = [None] + [torch.randn(B * S, generator=g).double().to(DEV) for _ in range(1, L)]
+            xb, yb, fb = x[idx].to(DEV), y[idx].to(DEV), fid[idx].to(DEV)
+            if B not in graphs:
+                graphs[B] = GraphedELBOStep(f1, o1, B, num_samples=S, static_eps=True)
+            l1, _ = graphs[B](xb, yb, fb, eps=eps)
+            l2, _ = f2(xb, yb, fb, eps=eps, num_samples=S)
+            o2.step()
+            assert relerr(l1, l2) < 1e-12, (epoch, a, relerr(l1, l2))
+    assert set(graphs) == {10, 6} and len(f1._ws) == 2 and f1._ws_pinned == {(10, S), (6, S)}
+    for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert relerr(a, b) < 1e-12, (n, relerr(a, b))
+    assert int(o1._step_dev) == 6
+
+
+def test_failed_step_is_skipped_by_adam_and_raised_at_check():
+    """A step whose Cholesky cannot be rescued by the three jitter retries leaves the parameters untouched (the Adam
+    kernel reads the step's failure flag on the device) and surfaces as NotPSDError at the next check()."""
+    from mobocmf_b200.errors import NotPSDError
+    from mobocmf_b200.fused import Adam, FusedELBOStep
+    from mobocmf_b200.mlls.variational_elbo_mf import VariationalELBOMF
+    L, S, B = 2, 1, 20
+    model, x, y, fid, N = make_model(L=L, M=32)
+    for l in range(L):
+        getattr(model, "hidden_layer_%d" % l).variational_strategy.jitter_val = -1e-2
+    step = FusedELBOStep(model, VariationalELBOMF(model, N, L))
+    opt = Adam([{"params": model.parameters()}], lr=0.01)
+    opt.skip_flag = step.skip_flag
+    before = [p.detach().clone() for p in model.parameters()]
+    g = torch.Generator().manual_seed(0)
+    idx = torch.randint(0, N, (B,), generator=g)
+    step(x[idx].to(DEV), y[idx].to(DEV), fid[idx].to(DEV))
+    opt.step()
+    for a, p in zip(before, model.parameters()):
+        assert torch.equal(a, p.detach())
+    assert step.retries() == 3
+    with pytest.raises(NotPSDError):
+        step.check()
+    # with the regular jitter the same objects step normally again (the sticky flags were cleared by check())
+    for l in range(L):
+        getattr(model, "hidden_layer_%d" % l).variational_strategy.jitter_val = 1e-6
+    step._sig = None
+    step(x[idx].to(DEV), y[idx].to(DEV), fid[idx].to(DEV))
+    opt.step()
+    step.check()
+    assert step.retries() == 0
+    assert any(not torch.equal(a, p.detach()) for a, p in zip(before, model.parameters()))

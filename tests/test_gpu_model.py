@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import mfdgp_oracle as O
-from tests.helpers import forrester_data, synthetic_data, oracle_view, relerr, parity_tol
+from tests.helpers import adjudicate_step, forrester_data, synthetic_data, oracle_view, relerr, parity_tol
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -84,14 +84,17 @@ def test_elbo_step_matches_oracle(case):
     print('cond %.2e tol %.1e loss relerr %.2e' % (cond, tol, relerr(loss, loss_o)))
     assert relerr(loss, loss_o) < tol
     assert relerr(res[1], fn.kl) < tol
+    if cond >= 1e5:
+        # the reference's default initialisation (cond ~ 1e7 - 1e8): fp64 itself loses digits in the gradients, which
+        # go through P^-1 twice.  The longdouble truth decides: the CUDA gradients must be as close to the exact
+        # answer as the reference-shaped fp64 oracle is (tests/helpers.adjudicate).
+        adjudicate_step(model, loss, grads_by_name(model), loss_o, g_o, L, xb, yb, fb, eps, N, 1)
+        return
     for n, gp in grads_by_name(model).items():
         go = g_o[n]
         if "chol_variational_covar" in n:
             gp, go = torch.tril(gp), torch.tril(go)
-        # gradients go through P^-1 twice: with the reference's default initialisation (cond ~ 1e7-1e8) only a
-        # loose agreement is meaningful in fp64; the well-conditioned variants carry the tight bar
-        gtol = 1e3 * tol if cond < 1e5 else 1e-2
-        assert relerr(gp, go) < gtol, (n, relerr(gp, go), gtol)
+        assert relerr(gp, go) < 1e3 * tol, (n, relerr(gp, go))
 
 
 def test_predict_for_acquisition_and_jes_match_oracle():
@@ -210,13 +213,15 @@ def test_only_highest_fidelity_model_matches_oracle():
     tol, cond = parity_tol(model)
     print("only-HF cond %.2e loss relerr %.2e" % (cond, relerr(loss, loss_o)))
     assert relerr(loss, loss_o) < tol
-    for n, p in model.named_parameters():
-        if not p.requires_grad:
-            continue
-        gp, go = p.grad, sd[n].grad
-        if "chol_variational_covar" in n:
-            gp, go = torch.tril(gp), torch.tril(go)
-        assert relerr(gp, go) < (1e3 * tol if cond < 1e5 else 1e-2), (n, relerr(gp, go))
+    if cond >= 1e5:
+        adjudicate_step(model, loss, {n: model.get_parameter(n).grad for n in names}, loss_o.detach(),
+                        {n: sd[n].grad for n in names}, L, xb, yb, fb, [None, None], N, 1, only_hf=True)
+    else:
+        for n in names:
+            gp, go = model.get_parameter(n).grad, sd[n].grad
+            if "chol_variational_covar" in n:
+                gp, go = torch.tril(gp), torch.tril(go)
+            assert relerr(gp, go) < 1e3 * tol, (n, relerr(gp, go))
     # acquisition path of the only-HF model
     model.eval()
     X = torch.rand(9, 1, 2, generator=g, dtype=torch.float64)
@@ -225,3 +230,46 @@ def test_only_highest_fidelity_model_matches_oracle():
     mu_o, var_o = O.predict_for_acquisition({k: v.detach() for k, v in sd.items()}, L, up, samples, X, 1,
                                             only_hf=True, noise_lower=lo)
     assert relerr(mu, mu_o) < tol and relerr(var, var_o) < 10 * tol
+
+
+def test_coupled_acq_float32_accumulator_matches_reference_semantics():
+    """Quirk Q8: the reference accumulates fp64 JES terms into a float32 tensor IN PLACE
+    (acquisition_functions/JESMOC_MFDGP.py:127-133): the sum is formed in fp64 and rounded to float32 once per term,
+    not round(term) + acc in float32 (which differs by one float32 ulp on ~6 % of the elements).  Exact equality with
+    the literal in-place loop on the same terms; agreement to one float32 ulp with the oracle's coupled_acq, whose
+    fp64 terms differ from the CUDA terms in the last fp64 digits."""
+    from mobocmf_b200.acquisition_functions.JESMOC_MFDGP import JESMOC_MFDGP, _JES_MFDGP
+    x, y, fid = synthetic_data([30, 20, 10], 2, seed=4)
+    L, K = 3, 3
+    g = torch.Generator().manual_seed(21)
+    pairs, mods_u, mods_c = [], [], []
+    for k in range(K):
+        mu = build(x, y, fid, L, seed=k, lengthscale=0.15)
+        mc = copy.deepcopy(mu)
+        with torch.no_grad():
+            for n, p in mc.named_parameters():
+                if "chol_variational_covar" in n:
+                    p.mul_(0.5 + 0.1 * k)
+        pairs.append((mu, mc))
+        for m_, lst in ((mu, mods_u), (mc, mods_c)):
+            sd, lo, up, samples = oracle_view(m_)
+            lst.append(dict(sd=sd, num_layers=L, noise_upper=up, noise_lower=lo, samples=samples))
+    X = torch.rand(500, 1, 2, generator=g, dtype=torch.float64)
+    acq = JESMOC_MFDGP.__new__(JESMOC_MFDGP)
+    for f in range(L):
+        acq.objectives = {f: {"o0": _JES_MFDGP(f, *pairs[0]), "o1": _JES_MFDGP(f, *pairs[1])}}
+        acq.constraints = {f: {"c0": _JES_MFDGP(f, *pairs[2])}}
+        with torch.no_grad():
+            val = acq.coupled_acq(X.to(DEV), f)
+            literal = torch.zeros(500, device=DEV, dtype=torch.float32)
+            for jes in list(acq.objectives[f].values()) + list(acq.constraints[f].values()):
+                literal += jes(X.to(DEV).double())                # the reference's line, verbatim semantics
+            val64 = acq.coupled_acq(X.to(DEV), f, float32_accumulator=False)
+        assert val.dtype == torch.float32 and torch.equal(val, literal)
+        ref = O.coupled_acq(mods_u, mods_c, X, f, float32_accumulator=True)
+        assert ref.dtype == torch.float32 and float(ref.max()) > 1e-3
+        ulp = torch.finfo(torch.float32).eps * ref.abs().clamp_min(1e-30)
+        diff = (val.cpu() - ref).abs()
+        assert bool((diff <= ulp).all()) and float((diff > 0).double().mean()) < 0.02
+        ref64 = O.coupled_acq(mods_u, mods_c, X, f, float32_accumulator=False)
+        assert val64.dtype == torch.float64 and (val64.cpu() - ref64).abs().max() < 1e-9

@@ -36,8 +36,13 @@ def test_multisample_elbo_and_grads():
     loss_o.backward()
     tol, cond = parity_tol(model)
     assert relerr(-res[0], loss_o) < tol and relerr(res[1], kl_o) < tol
+    if cond >= 1e5:       # ill-conditioned: adjudicated by the longdouble truth (tests/helpers.adjudicate)
+        from tests.helpers import adjudicate_step
+        adjudicate_step(model, -res[0], {n: p.grad for n, p in model.named_parameters()}, loss_o.detach(),
+                        {n: sd[n].grad for n in names}, L, x[idx], y[idx], fid[idx], eps, N, S)
+        return
     for n, p in model.named_parameters():
         gp, go = p.grad, sd[n].grad
         if "chol_variational_covar" in n:
             gp, go = torch.tril(gp), torch.tril(go)
-        assert relerr(gp, go) < (1e3 * tol if cond < 1e5 else 1e-2), (n, relerr(gp, go))
+        assert relerr(gp, go) < 1e3 * tol, (n, relerr(gp, go))
