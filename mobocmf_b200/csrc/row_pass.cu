@@ -20,6 +20,19 @@
 
 namespace mobo {
 
+// ---- optional per-phase cycle accounting of the row kernels (tools/row_bench.cu builds with -DROW_TIMING) ----
+#ifdef ROW_TIMING
+__device__ unsigned long long row_times[3][512][16];
+#define RT_DECL __shared__ unsigned long long rt_acc[16]; unsigned long long rt_prev = clock64(); \
+  if (threadIdx.x == 0) for (int k_ = 0; k_ < 16; ++k_) rt_acc[k_] = 0ull;
+#define RT_TICK(k) do { if (threadIdx.x == 0) { const unsigned long long n_ = clock64(); rt_acc[k] += n_ - rt_prev; rt_prev = n_; } } while (0)
+#define RT_FLUSH(which) do { if (threadIdx.x == 0 && blockIdx.x < 512) for (int k_ = 0; k_ < 16; ++k_) row_times[which][blockIdx.x][k_] = rt_acc[k_]; } while (0)
+#else
+#define RT_DECL
+#define RT_TICK(k)
+#define RT_FLUSH(which)
+#endif
+
 constexpr int TR = 32;             // rows per tile
 constexpr int ROW_THREADS = 256;   // 8 warps: one per pair of 16-row operator slabs at MP = 256
 constexpr int ROW_WARPS = ROW_THREADS / 32;
@@ -120,6 +133,7 @@ struct CovSmem {
 
 struct RowSmem : CovSmem<ROW_WARPS, false> {
   double red[3][NCH_MAX][TR];     // per warp-pair partial column sums: q1, mu, q2
+  int xsel[TR];                   // tile-shared covariance build: which of the tile's distinct x rows a tile row reads
 };
 static_assert(ROW_WARPS * RPW == TR, "the covariance build maps RPW rows to each warp of the row tile");
 
@@ -321,14 +335,15 @@ __device__ inline void load_kern_fast(KernFast& kf, int kind, int d, const doubl
 }
 
 template <class SM>
-__device__ __forceinline__ void load_inducing(const RowArgs& a, SM& sm) {
+__device__ __forceinline__ void load_inducing(const RowArgs& a, SM& sm, bool with_zx = true) {
   const int tid = threadIdx.x;
   if (tid == 0) load_kern_fast(sm.kf, a.kind, a.d, a.theta);
   if (tid >= 32 && tid < 32 + kExp2Tab) sm.e2tab[tid - 32] = exp2((double)(tid - 32) / kExp2Tab);
-  for (int idx = tid; idx < a.MP * a.d; idx += SM::THREADS) {
-    const int j = idx / a.d, c = idx - j * a.d;
-    sm.zsT[c][j] = j < a.M ? a.Zx[(size_t)j * a.d + c] : 0.0;
-  }
+  if (with_zx)
+    for (int idx = tid; idx < a.MP * a.d; idx += SM::THREADS) {
+      const int j = idx / a.d, c = idx - j * a.d;
+      sm.zsT[c][j] = j < a.M ? a.Zx[(size_t)j * a.d + c] : 0.0;
+    }
   for (int j = tid; j < a.MP; j += SM::THREADS) sm.zfs[j] = (a.kind == 1 && j < a.M) ? a.zf[j] : 0.0;
 }
 
@@ -411,6 +426,98 @@ __device__ __forceinline__ bool warp_rows_share_x(const RowArgs& a, long long ro
   return a.xrep > 1 && r0 / a.xrep == (r0 + RPW - 1) / a.xrep;
 }
 
+// The general covariance build of the forward kernel (layer 0, and upper layers whose rows do not share x in large
+// groups: single-sample training, small S).  Kept out of line: its per-dimension register arrays (up to 8 dimensions
+// x 4 rows) would otherwise set the register allocation of the whole kernel, whose hot configuration (xshare, below)
+// needs none of them.
+__device__ __noinline__ void build_k_tile_generic(const RowArgs& a, const RowSmem& sm, double* Ks, int ldb, unsigned row0,
+                                                  int nvalid, int warp, int lane) {
+  if (a.kind == 0) build_k_tile_d<0, false>(sm, Ks, ldb, a.M, a.MP, nvalid, warp, lane);
+  else if (warp_rows_share_x(a, row0, warp)) build_k_tile_d<1, true>(sm, Ks, ldb, a.M, a.MP, nvalid, warp, lane);
+  else build_k_tile_d<1, false>(sm, Ks, ldb, a.M, a.MP, nvalid, warp, lane);
+}
+
+// ---- A-fragment stream of the forward kernel ------------------------------------------------------------------------
+// A tile's two triangular products are four "segments" per warp (W slab A, W slab B, H^T slab A, H^T slab B), each a run
+// of k-steps whose A fragments this lane streams from L2 through its private cp.async ring.  The ring never drains: the
+// last k-steps of a segment already fetch the first fragments of the NEXT segment (and the last segment of a tile those
+// of the next tile's first), so a segment starts with its first NST - 1 fragments in flight instead of paying an L2
+// round trip (4 per tile in the first version).  Every segment is a multiple of NST = 4 k-steps, so the slot of k-step q
+// is q & 3 in every segment.  One k-step: 1 fragment copy issued, 1 fragment read, 4 B loads, 8 DMMAs.
+// The 16 x 16 diagonal block of a slab is half zeros (the operators are triangular): its two k-steps that only touch
+// the zero half of one 8-row group skip that group's DMMAs (LOWER: rows 0-7 x k 8-15, the slab's last k-steps; UPPER:
+// rows 8-15 x k 0-7, its first ones): 16 of a slab pair's 544 DMMAs per product.
+constexpr int SKIP_NONE = 0, SKIP_LOW_DIAG = 1, SKIP_UP_DIAG = 2;
+
+template <int SKIP, bool CHAIN>
+__device__ __forceinline__ void frag_group(double (&acc)[2][4][2], const double2* __restrict__ ap,
+                                           const double2* __restrict__ nextp, const double* __restrict__ bp,
+                                           size_t ct_stride, double2* slot) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    // k-step j + 3 of this run: in this segment, or (CHAIN: the segment's last group) fragment j - 1 of the next one
+    const double2* src = (CHAIN && j >= 1) ? nextp + (j - 1) * 32 : ap + (j + 3) * 32;
+    cp_async16_cg(slot + ((j + 3) & 3) * 32, src);
+    cp_async_commit_group();
+    cp_async_wait_group<3>();
+    const double2 av = slot[j * 32];
+    const bool do0 = !(SKIP == SKIP_LOW_DIAG && j >= 2), do1 = !(SKIP == SKIP_UP_DIAG && j < 2);
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct) {
+      const double b = bp[ct * ct_stride + 4 * j];
+      if (do0) dmma884(acc[0][ct][0], acc[0][ct][1], av.x, b);
+      if (do1) dmma884(acc[1][ct][0], acc[1][ct][1], av.y, b);
+    }
+  }
+}
+
+// one segment: acc(16 rows x 32 cols) += A[slab s, its triangular k-range] * B.  The ring must already hold (or have in
+// flight) the segment's first 3 fragments; on return it holds those of the segment starting at `nextp`.
+template <bool UPPER>
+__device__ __forceinline__ void frag_segment(double (&acc)[2][4][2], const double* __restrict__ Af, int MP, const double* Bs,
+                                             int ldb, int s, int half, int lane, double2* ring,
+                                             const double2* __restrict__ nextp) {
+  const int g = lane >> 2, t = lane & 3;
+  const int kbeg = UPPER ? 16 * s : 0;
+  const int nq = (UPPER ? MP - 16 * s : 16 * (s + 1)) >> 2;        // k-steps: a multiple of 4
+  double2* slot = ring + lane;
+  const double2* ap = reinterpret_cast<const double2*>(Af) + ((size_t)s * (MP >> 2) + (kbeg >> 2)) * 32 + lane;
+  const double* bp = Bs + (size_t)(32 * half + g) * ldb + t + kbeg;
+  const size_t ct_stride = (size_t)8 * ldb;
+  if (UPPER) {
+    if (nq == 4) { frag_group<SKIP_UP_DIAG, true>(acc, ap, nextp, bp, ct_stride, slot); return; }
+    frag_group<SKIP_UP_DIAG, false>(acc, ap, nextp, bp, ct_stride, slot);
+    ap += 4 * 32; bp += 16;
+    for (int q0 = 4; q0 < nq - 4; q0 += 4) {
+      frag_group<SKIP_NONE, false>(acc, ap, nextp, bp, ct_stride, slot);
+      ap += 4 * 32; bp += 16;
+    }
+    frag_group<SKIP_NONE, true>(acc, ap, nextp, bp, ct_stride, slot);
+  } else {
+    for (int q0 = 0; q0 < nq - 4; q0 += 4) {
+      frag_group<SKIP_NONE, false>(acc, ap, nextp, bp, ct_stride, slot);
+      ap += 4 * 32; bp += 16;
+    }
+    frag_group<SKIP_LOW_DIAG, true>(acc, ap, nextp, bp, ct_stride, slot);
+  }
+}
+
+__device__ __forceinline__ const double2* frag_start(const double* Af, int MP, int s, bool upper, int lane) {
+  return reinterpret_cast<const double2*>(Af) + ((size_t)s * (MP >> 2) + (upper ? 4 * s : 0)) * 32 + lane;
+}
+
+// Distinct x rows a 32-row tile may hold for the tile-shared covariance build (below); xrep >= 11 guarantees it
+constexpr int XMAX = 4, XSHARE_MIN_REP = 11;
+
+// Forward row pass.  Per 32-row tile (two CTAs per SM, 8 warps each):
+//   rows (prefetched one tile ahead into registers) -> shared;  K(Z_l, rows) into the tile buffer;  t = W k (DMMA);
+//   t -> tile buffer (bulk-stored to Tsave from there);  u = H^T t (DMMA), stored from the accumulators;  mean / variance.
+// Covariance build when the rows are MC samples of few points (xrep >= 11: at most XMAX = 4 distinct x per tile; the
+// S = 64 training tiles have one, the S = 25 acquisition tiles two or three): the two x-kernels a1 E1, a2 E2 depend on
+// (x, z_j) only, so thread j evaluates them ONCE per tile and distinct x into shared memory, and the per-(row, j) work
+// shrinks to the f-kernel: one exponential instead of three (and no per-dimension arithmetic).  In the first version
+// every warp re-evaluated them for its own 4 rows (8x redundant at S = 64) and the build - DFMA work on the FP64 pipe
+// the co-resident CTA's DMMAs are hogging - was 30 % of a CTA's time (tools/row_bench -DROW_TIMING).
 __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(const __grid_constant__ RowArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RowSmem& sm = *reinterpret_cast<RowSmem*>(smem_raw);
@@ -426,26 +533,147 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
   const double* W = a.ops + ops_block(MP, OPS_WF);
   const double* G = a.ops + ops_block(MP, OPS_HTF);
   const double* beta = a.ops + ops_beta(MP);
+  // tile-shared covariance build: decided per launch (the shared x-kernel values live where the legacy build keeps Z^T)
+  const bool xshare = a.kind == 1 && a.xrep >= XSHARE_MIN_REP;
+  double (*s1s)[MAX_MP] = sm.zsT;            // [XMAX][MAX_MP]  a1 E1(x_c, z_j)
+  double (*s2s)[MAX_MP] = sm.zsT + XMAX;     // [XMAX][MAX_MP]  a2 E2(x_c, z_j)
+  static_assert(2 * XMAX <= kMaxD, "the shared x-kernel values overlay zsT");
 
-  load_inducing(a, sm);
+  RT_DECL
+  load_inducing(a, sm, !xshare);
+  double bi[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  if (active) {
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+      for (int ib = 0; ib < 2; ++ib) bi[sl][ib] = __ldg(beta + 16 * (sl == 0 ? sA : sB) + 8 * ib + g);
+  }
+
+  // ---- row data, prefetched one tile ahead: threads 0..31 hold a row's (mean, variance, normal) or its direct f,
+  //      threads 32.. one coordinate of one of the tile's distinct x rows (xshare) ----
+  // (row indices are 32-bit here: the launcher refuses R >= 2^31, callers chunk long before that)
+  const unsigned R = (unsigned)a.R, ntiles = (R + TR - 1) / TR;
+  const unsigned uxrep = (unsigned)a.xrep, uprep = (unsigned)a.prep;
+  const unsigned ueps = a.eps_mod >= a.R ? 0u : (unsigned)a.eps_mod;       // 0: eps index == row
+  double pf_a = 0.0, pf_b = 1.0, pf_c = 0.0;
+  auto prefetch = [&](unsigned tile) {
+    if (tile >= ntiles) return;
+    const unsigned row0 = tile * TR;
+    if (tid < TR) {
+      const unsigned row = row0 + tid;
+      pf_a = 0.0; pf_b = 1.0; pf_c = 0.0;
+      if (row < R && a.kind == 1) {
+        if (a.f_direct) {
+          pf_a = a.f_direct[row];
+        } else {
+          const unsigned pr = row / uprep;
+          pf_a = a.mu_prev[pr];
+          pf_b = a.var_prev[pr];
+          pf_c = a.eps[ueps ? row % ueps : row];
+        }
+      }
+    } else if (xshare && tid < TR + XMAX * a.d) {
+      const int c = (tid - TR) / a.d, cc = (tid - TR) - c * a.d;
+      const unsigned xi = row0 / uxrep + c;
+      const unsigned last = min(R - 1, row0 + TR - 1) / uxrep;
+      pf_a = xi <= last ? a.x[(size_t)xi * a.d + cc] : 0.0;
+    }
+  };
+  prefetch(blockIdx.x);
+  // ring: the first 3 fragments of the first segment (every later segment is primed by its predecessor)
+  if (active) {
+    const double2* first = frag_start(W, MP, sA, false, lane);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { cp_async16_cg(ring + lane + j * 32, first + j * 32); cp_async_commit_group(); }
+  }
   __syncthreads();
+  RT_TICK(0);
 
-  const long long ntiles = (a.R + TR - 1) / TR;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long row0 = tile * TR;
-    const int nvalid = (int)min((long long)TR, a.R - row0);
-    load_tile_rows(a, sm, row0, nvalid);
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const unsigned row0 = tile * TR;
+    const int nvalid = (int)min((unsigned)TR, R - row0);
+    const unsigned xi0 = row0 / uxrep;
+    // ---- this tile's rows: registers -> shared ----
+    if (tid < TR) {
+      double f = 0.0;
+      if (tid < nvalid && a.kind == 1) f = a.f_direct ? pf_a : pf_a + sqrt(fmax(pf_b, kMinVariance)) * pf_c;
+      sm.fs[tid] = f;
+      sm.kxx[tid] = sm.kf.kind == 0 ? sm.kf.a1 : sm.kf.a1 * (sm.kf.vlin * f * f + sm.kf.af) + sm.kf.a2;
+      sm.xsel[tid] = tid < nvalid ? (int)((row0 + tid) / uxrep - xi0) : 0;
+    } else if (xshare) {
+      if (tid < TR + XMAX * a.d) { const int c = (tid - TR) / a.d; sm.xs[c][(tid - TR) - c * a.d] = pf_a; }
+    }
+    if (!xshare) {
+      for (int idx = tid; idx < TR * a.d; idx += ROW_THREADS) {
+        const int r = idx / a.d, c = idx - r * a.d;
+        sm.xs[r][c] = r < nvalid ? a.x[(size_t)((row0 + r) / uxrep) * a.d + c] : 0.0;
+      }
+    }
     __syncthreads();
+    prefetch(tile + gridDim.x);         // lands during the products
+    RT_TICK(1);
     // ---- K(Z_l, rows) into shared memory ----
-    if (a.kind == 0) build_k_tile_d<0, false>(sm, Ks, ldb, a.M, MP, nvalid, warp, lane);
-    else if (warp_rows_share_x(a, row0, warp)) build_k_tile_d<1, true>(sm, Ks, ldb, a.M, MP, nvalid, warp, lane);
-    else build_k_tile_d<1, false>(sm, Ks, ldb, a.M, MP, nvalid, warp, lane);
+    if (xshare) {
+      // (a) thread j: a1 E1 and a2 E2 between inducing point j and each distinct x of the tile
+      const int nx = (int)((row0 + nvalid - 1) / uxrep - xi0) + 1;
+      if (tid < MP) {
+        const KernFast& kf = sm.kf;
+        const bool jok = tid < a.M;
+        double D1[XMAX], D2[XMAX];
+#pragma unroll
+        for (int q = 0; q < XMAX; ++q) { D1[q] = kf.la1; D2[q] = kf.la2; }
+        for (int c = 0; c < a.d; ++c) {          // dimensions in ascending order, like every other build of K
+          const double z = jok ? __ldg(a.Zx + (size_t)tid * a.d + c) : 0.0;
+          const double2 cc = kf.cc[c];
+#pragma unroll
+          for (int q = 0; q < XMAX; ++q)
+            if (q < nx) {
+              const double df = sm.xs[q][c] - z;
+              const double d2 = df * df;
+              D1[q] = fma(d2, cc.x, D1[q]);
+              D2[q] = fma(d2, cc.y, D2[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < XMAX; ++q)
+          if (q < nx) {
+            s1s[q][tid] = jok ? exp2_tab(D1[q], sm.e2tab) : 0.0;
+            s2s[q][tid] = jok ? exp2_tab(D2[q], sm.e2tab) : 0.0;
+          }
+      }
+      __syncthreads();
+      // (b) warp <-> RPW rows, lane <-> inducing point of a 32-chunk: k = s1 (v f z_f + a_f E_f) + s2
+      const KernFast& kf = sm.kf;
+      const int rbase = warp * RPW;
+      double f[RPW], vf[RPW];
+      int xs_[RPW];
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) { f[i] = sm.fs[rbase + i]; vf[i] = kf.vlin * f[i]; xs_[i] = sm.xsel[rbase + i]; }
+      const double laf = kf.laf, cf = kf.cf;
+      for (int ch = 0; ch < MP / 32; ++ch) {
+        const int j = 32 * ch + lane;
+        const double zf = sm.zfs[j];
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+          const double dff = f[i] - zf;
+          const double Ef = exp2_tab(fma(dff * dff, cf, laf), sm.e2tab);
+          const double k = fma(s1s[xs_[i]][j], fma(vf[i], zf, Ef), s2s[xs_[i]][j]);
+          Ks[(size_t)(rbase + i) * ldb + j] = rbase + i < nvalid ? k : 0.0;
+        }
+      }
+    } else {
+      build_k_tile_generic(a, sm, Ks, ldb, row0, nvalid, warp, lane);
+    }
+    RT_TICK(2);
     __syncthreads();
+    RT_TICK(3);
     // ---- t = W k ----
     double acc[2][2][4][2];
     zero_acc(acc);
     if (active) {
-      slab_gemm<false, FWD_NST>(acc, W, MP, Ks, ldb, sA, sB, half, lane, ring);
+      frag_segment<false>(acc[0], W, MP, Ks, ldb, sA, half, lane, ring, frag_start(W, MP, sB, false, lane));
+      frag_segment<false>(acc[1], W, MP, Ks, ldb, sB, half, lane, ring, frag_start(G, MP, sA, true, lane));
+      RT_TICK(4);
       double pq[4][2], pm[4][2];
 #pragma unroll
       for (int ct = 0; ct < 4; ++ct)
@@ -455,14 +683,13 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
       for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
         for (int ib = 0; ib < 2; ++ib) {
-          const double bi = __ldg(beta + 16 * (sl == 0 ? sA : sB) + 8 * ib + g);
 #pragma unroll
           for (int ct = 0; ct < 4; ++ct)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const double v = acc[sl][ib][ct][e];
               pq[ct][e] = fma(v, v, pq[ct][e]);
-              pm[ct][e] = fma(bi, v, pm[ct][e]);
+              pm[ct][e] = fma(bi[sl][ib], v, pm[ct][e]);
             }
         }
 #pragma unroll
@@ -481,9 +708,12 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
           }
         }
     }
+    RT_TICK(5);
     __syncthreads();   // every warp is done reading K
+    RT_TICK(6);
     if (active) store_acc_to_tile(acc, Ks, ldb, sA, sB, half, lane);
     __syncthreads();
+    RT_TICK(7);
     // whitened rows t = W k, row-major [R][MP], for the backward (SYRK statistics and dt): one bulk (TMA engine)
     // shared -> global copy per row, issued by warp 0, instead of 32 shared loads + 32 global stores per thread; the
     // copies read the tile while the second product does, and are waited for before the tile is rebuilt
@@ -491,7 +721,7 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes of t -> async-proxy reads
       if (lane < nvalid)
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
-                         a.Tsave + (size_t)(row0 + lane) * MP),
+                         a.Tsave + (size_t)(row0 + (unsigned)lane) * MP),
                      "r"((unsigned)__cvta_generic_to_shared(Ks + (size_t)lane * ldb)),
                      "r"((unsigned)(MP * sizeof(double))) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -499,7 +729,9 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
     // ---- u = H^T t ----
     if (active) {
       zero_acc(acc);
-      slab_gemm<true, FWD_NST>(acc, G, MP, Ks, ldb, sA, sB, half, lane, ring);
+      frag_segment<true>(acc[0], G, MP, Ks, ldb, sA, half, lane, ring, frag_start(G, MP, sB, true, lane));
+      frag_segment<true>(acc[1], G, MP, Ks, ldb, sB, half, lane, ring, frag_start(W, MP, sA, false, lane));
+      RT_TICK(8);
 #pragma unroll
       for (int ct = 0; ct < 4; ++ct)
 #pragma unroll
@@ -515,7 +747,9 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
         }
       if (a.Usave) store_acc_rows(acc, a.Usave, row0, nvalid, MP, sA, sB, half, lane);
     }
+    RT_TICK(9);
     __syncthreads();
+    RT_TICK(10);
     if (tid < nvalid) {
       double q1 = 0.0, mu = 0.0, q2 = 0.0;
       for (int pp = 0; pp < npairs; ++pp) {
@@ -532,7 +766,312 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
     }
     if (a.Tsave && warp == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();
+    RT_TICK(11);
   }
+  cp_async_wait_group<0>();     // the chained look-ahead of the last segment
+  RT_FLUSH(0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised forward kernel: the hot configuration (upper layers whose rows are MC samples of few points: the
+// S-sample training tiles and the acquisition tiles; `xshare`).
+//
+// What the measurements said (tools/row_bench -DROW_TIMING, profiles/r02_row_fwd_phases.txt):
+//  * DFMA and DMMA share the FP64 pipe and the schedulers arbitrate between warps, not work: next to a warp that
+//    streams DMMAs (16 pipe cycles each) a covariance-build warp gets ONE FP64 instruction through per 36 - 72 cycles.
+//    With two co-resident CTAs the build was 23 - 30 % of a CTA's time and the pipe idled 26 % of the time - whenever
+//    both CTAs were outside their products at once (their phases drift freely).
+//  * a ping-pong of two 8-warp groups with a pipe token did not help: the group outside the token (building) is starved
+//    so thoroughly that it is not ready when the token comes back.
+//  * a lone CTA's products run at 89 % of the pipe.
+// So: ONE CTA per SM, 8 PRODUCT warps that do nothing but the two triangular DMMA products tile after tile (plus the
+// accumulator -> shared-memory hand-overs), and 8 SUPPORT warps that do everything else one tile ahead / behind, out
+// of the products' way - starved, but with a whole tile period for half a period of work:
+//     support:  rows (prefetched), K(Z, rows) of tile i+1 into the other tile buffer | row sums of t(i), bulk store
+//               of t(i) | row sums of u(i-1), bulk store of u(i-1), mean / variance of tile i-1
+//     product:  t = W k | t -> tile (in place of K) | u = H^T t | u -> tile (in place of t)
+// Two tile buffers, each cycling K -> t -> u; eight named barriers hand them over (arrive by the producer group, sync
+// by the consumer group).  The row sums |t|^2, beta.t, |u|^2 are taken from shared memory by the support warps (the
+// first version reduced them from the accumulators with 48 shuffles per thread inside the product warps), and u leaves
+// as one bulk copy per row like t (it used to be 32 scattered 8-byte stores per thread).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int WS_THREADS = 2 * ROW_THREADS;
+struct WsSmem {
+  KernFast kf;
+  double e2tab[kExp2Tab];
+  double zfs[MAX_MP];
+  double beta[MAX_MP];
+  double fs[TR];
+  int xsel[TR];
+  double xs[XMAX][kMaxD];
+  double kxx[2][TR], q1[2][TR], mu[2][TR];     // per tile buffer
+  double s12[2 * XMAX][MAX_MP];                 // [0, XMAX): a1 E1(x_c, z_j);  [XMAX, 2 XMAX): a2 E2(x_c, z_j)
+};
+__host__ __device__ inline size_t ws_head_bytes() { return ((sizeof(WsSmem) + 127) / 128) * 128; }
+__host__ inline size_t ws_smem_bytes(int MP) {
+  return ws_head_bytes() + 2 * tile_bytes(MP) + (size_t)ROW_WARPS * FWD_NST * 32 * sizeof(double2);
+}
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// named barriers: 1 product group, 2 support group, then per tile buffer b (0 / 1):
+constexpr int WS_BAR_PROD = 1, WS_BAR_SUPP = 2;
+constexpr int WS_K_READY = 3;    // + b  support -> product: K(Z, rows) is in the buffer
+constexpr int WS_T_READY = 5;    // + b  product -> support: t has replaced K
+constexpr int WS_T_DONE = 7;     // + b  support -> product: t's row sums and bulk store are done, u may replace it
+constexpr int WS_U_READY = 9;    // + b  product -> support: u has replaced t
+
+__global__ void __launch_bounds__(WS_THREADS, 1) row_fwd_ws_kernel(const __grid_constant__ RowArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_raw);
+  const int MP = a.MP, ldb = MP + 4;
+  const bool support = threadIdx.x >= ROW_THREADS;
+  const int tid = threadIdx.x & (ROW_THREADS - 1), lane = tid & 31, warp = tid >> 5;
+  double* tiles = reinterpret_cast<double*>(smem_raw + ws_head_bytes());
+  auto tile_buf = [&](int b) { return tiles + (size_t)b * (tile_bytes(MP) / sizeof(double)); };
+  const unsigned R = (unsigned)a.R, ntiles = (R + TR - 1) / TR;
+  const unsigned n = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;   // this CTA's tiles
+
+  RT_DECL
+  // ---- data shared by both groups ----
+  if (threadIdx.x == 0) load_kern_fast(sm.kf, a.kind, a.d, a.theta);
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + kExp2Tab) sm.e2tab[threadIdx.x - 32] = exp2((double)(threadIdx.x - 32) / kExp2Tab);
+  for (int j = threadIdx.x; j < MP; j += WS_THREADS) {
+    sm.zfs[j] = j < a.M ? a.zf[j] : 0.0;
+    sm.beta[j] = (a.ops + ops_beta(MP))[j];
+  }
+  __syncthreads();
+  RT_TICK(0);
+
+  if (!support) {
+    // =========================== product warps ===========================
+    double2* ring = reinterpret_cast<double2*>(smem_raw + ws_head_bytes() + 2 * tile_bytes(MP)) + warp * FWD_NST * 32;
+    const int p = warp, npairs = MP / 32, ns = MP / 16;
+    const bool active = p < npairs;
+    const int sA = p, sB = ns - 1 - p;
+    const double* W = a.ops + ops_block(MP, OPS_WF);
+    const double* G = a.ops + ops_block(MP, OPS_HTF);
+    if (active) {
+      const double2* f0 = frag_start(W, MP, sA, false, lane);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { cp_async16_cg(ring + lane + j * 32, f0 + j * 32); cp_async_commit_group(); }
+    }
+    for (unsigned i = 0; i < n; ++i) {
+      const int b = i & 1;
+      double* Ks = tile_buf(b);
+      double acc[2][2][4][2];
+      bar_sync(WS_K_READY + b, WS_THREADS);
+      RT_TICK(1);
+      // ---- t = W k ----
+      zero_acc(acc);
+      if (active) {
+        frag_segment<false>(acc[0], W, MP, Ks, ldb, sA, 0, lane, ring, frag_start(W, MP, sB, false, lane));
+        frag_segment<false>(acc[1], W, MP, Ks, ldb, sB, 0, lane, ring, frag_start(G, MP, sA, true, lane));
+      }
+      RT_TICK(2);
+      bar_sync(WS_BAR_PROD, ROW_THREADS);   // every product warp is done reading K
+      if (active) store_acc_to_tile(acc, Ks, ldb, sA, sB, 0, lane);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // t is bulk-copied out by the support warps
+      bar_sync(WS_BAR_PROD, ROW_THREADS);
+      bar_arrive(WS_T_READY + b, WS_THREADS);
+      RT_TICK(3);
+      // ---- u = H^T t ----
+      zero_acc(acc);
+      if (active) {
+        frag_segment<true>(acc[0], G, MP, Ks, ldb, sA, 0, lane, ring, frag_start(G, MP, sB, true, lane));
+        frag_segment<true>(acc[1], G, MP, Ks, ldb, sB, 0, lane, ring, frag_start(W, MP, sA, false, lane));
+      }
+      RT_TICK(4);
+      bar_sync(WS_T_DONE + b, WS_THREADS);  // all product warps are done reading t, and so are the support warps
+      RT_TICK(5);
+      if (active) store_acc_to_tile(acc, Ks, ldb, sA, sB, 0, lane);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      bar_sync(WS_BAR_PROD, ROW_THREADS);
+      bar_arrive(WS_U_READY + b, WS_THREADS);
+      RT_TICK(6);
+    }
+    cp_async_wait_group<0>();     // the chained look-ahead of the last segment
+    RT_FLUSH(0);
+    return;
+  }
+
+  // =========================== support warps ===========================
+  const unsigned uxrep = (unsigned)a.xrep, uprep = (unsigned)a.prep;
+  const unsigned ueps = a.eps_mod >= a.R ? 0u : (unsigned)a.eps_mod;       // 0: eps index == row
+  double (*s1s)[MAX_MP] = sm.s12;
+  double (*s2s)[MAX_MP] = sm.s12 + XMAX;
+  auto ssync = [&]() { bar_sync(WS_BAR_SUPP, ROW_THREADS); };
+  auto tile_of = [&](unsigned i) { return blockIdx.x + i * gridDim.x; };
+  // row data of the tile after the one being built, prefetched into registers: threads 0..31 a row's (mean, variance,
+  // normal) or its direct f, threads 32.. one coordinate of one of the tile's distinct x rows
+  double pf_a = 0.0, pf_b = 1.0, pf_c = 0.0;
+  auto prefetch = [&](unsigned i) {
+    if (i >= n) return;
+    const unsigned row0 = tile_of(i) * TR;
+    if (tid < TR) {
+      const unsigned row = row0 + tid;
+      pf_a = 0.0; pf_b = 1.0; pf_c = 0.0;
+      if (row < R) {
+        if (a.f_direct) {
+          pf_a = a.f_direct[row];
+        } else {
+          const unsigned pr = row / uprep;
+          pf_a = a.mu_prev[pr];
+          pf_b = a.var_prev[pr];
+          pf_c = a.eps[ueps ? row % ueps : row];
+        }
+      }
+    } else if (tid < TR + XMAX * a.d) {
+      const int c = (tid - TR) / a.d, cc = (tid - TR) - c * a.d;
+      const unsigned xi = row0 / uxrep + c;
+      const unsigned last = min(R - 1, row0 + TR - 1) / uxrep;
+      pf_a = xi <= last ? a.x[(size_t)xi * a.d + cc] : 0.0;
+    }
+  };
+  // K(Z_l, rows of tile i) into buffer i & 1 (its previous contents must have been released)
+  auto build = [&](unsigned i) {
+    const int b = i & 1;
+    double* Ks = tile_buf(b);
+    const unsigned row0 = tile_of(i) * TR;
+    const int nvalid = (int)min((unsigned)TR, R - row0);
+    const unsigned xi0 = row0 / uxrep;
+    if (tid < TR) {
+      double f = 0.0;
+      if (tid < nvalid) f = a.f_direct ? pf_a : pf_a + sqrt(fmax(pf_b, kMinVariance)) * pf_c;
+      sm.fs[tid] = f;
+      sm.kxx[b][tid] = sm.kf.a1 * (sm.kf.vlin * f * f + sm.kf.af) + sm.kf.a2;
+      sm.xsel[tid] = tid < nvalid ? (int)((row0 + tid) / uxrep - xi0) : 0;
+    } else if (tid < TR + XMAX * a.d) {
+      const int c = (tid - TR) / a.d;
+      sm.xs[c][(tid - TR) - c * a.d] = pf_a;
+    }
+    ssync();
+    prefetch(i + 1);
+    // (a) thread j: a1 E1 and a2 E2 between inducing point j and each distinct x of the tile
+    const int nx = (int)((row0 + nvalid - 1) / uxrep - xi0) + 1;
+    if (tid < MP) {
+      const KernFast& kf = sm.kf;
+      const bool jok = tid < a.M;
+      double D1[XMAX], D2[XMAX];
+#pragma unroll
+      for (int q = 0; q < XMAX; ++q) { D1[q] = kf.la1; D2[q] = kf.la2; }
+      for (int c = 0; c < a.d; ++c) {          // dimensions in ascending order, like every other build of K
+        const double z = jok ? __ldg(a.Zx + (size_t)tid * a.d + c) : 0.0;
+        const double2 cc = kf.cc[c];
+#pragma unroll
+        for (int q = 0; q < XMAX; ++q)
+          if (q < nx) {
+            const double df = sm.xs[q][c] - z;
+            const double d2 = df * df;
+            D1[q] = fma(d2, cc.x, D1[q]);
+            D2[q] = fma(d2, cc.y, D2[q]);
+          }
+      }
+#pragma unroll
+      for (int q = 0; q < XMAX; ++q)
+        if (q < nx) {
+          s1s[q][tid] = jok ? exp2_tab(D1[q], sm.e2tab) : 0.0;
+          s2s[q][tid] = jok ? exp2_tab(D2[q], sm.e2tab) : 0.0;
+        }
+    }
+    ssync();
+    // (b) warp <-> RPW rows, lane <-> inducing point of a 32-chunk: k = s1 (v f z_f + a_f E_f) + s2
+    {
+      const KernFast& kf = sm.kf;
+      const int rbase = warp * RPW;
+      double f[RPW], vf[RPW];
+      int xs_[RPW];
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) { f[r] = sm.fs[rbase + r]; vf[r] = kf.vlin * f[r]; xs_[r] = sm.xsel[rbase + r]; }
+      const double laf = kf.laf, cf = kf.cf;
+      for (int ch = 0; ch < MP / 32; ++ch) {
+        const int j = 32 * ch + lane;
+        const double zf = sm.zfs[j];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          const double dff = f[r] - zf;
+          const double Ef = exp2_tab(fma(dff * dff, cf, laf), sm.e2tab);
+          const double k = fma(s1s[xs_[r]][j], fma(vf[r], zf, Ef), s2s[xs_[r]][j]);
+          Ks[(size_t)(rbase + r) * ldb + j] = rbase + r < nvalid ? k : 0.0;
+        }
+      }
+    }
+    ssync();      // also: fs / xsel / s12 are free for the next build
+    bar_arrive(WS_K_READY + b, WS_THREADS);
+  };
+  // row sums over the tile in shared memory: thread <-> (row = tid / 8, columns tid % 8 + 8 k); 8-lane fold
+  const int srow = tid >> 3, spart = tid & 7;
+  auto fold8 = [&](double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+  };
+  // bulk (TMA engine) copies of the tile's valid rows to dst[R][MP], issued by the group's warp 0, which also waits
+  // until the engine has read them (the buffer is rewritten next)
+  auto bulk_rows_out = [&](double* dst, const double* Ks, unsigned row0, int nvalid) {
+    if (warp == 0) {
+      if (lane < nvalid)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                         dst + (size_t)(row0 + (unsigned)lane) * MP),
+                     "r"((unsigned)__cvta_generic_to_shared(Ks + (size_t)lane * ldb)),
+                     "r"((unsigned)(MP * sizeof(double))) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  };
+  auto bulk_wait_read = [&]() { if (warp == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); };
+  // t of tile i is in its buffer: |t|^2 and beta . t per row, bulk store of t; then u may replace it
+  auto finish_t = [&](unsigned i) {
+    const int b = i & 1;
+    const double* Ks = tile_buf(b);
+    const unsigned row0 = tile_of(i) * TR;
+    const int nvalid = (int)min((unsigned)TR, R - row0);
+    bar_sync(WS_T_READY + b, WS_THREADS);
+    if (a.Tsave) bulk_rows_out(a.Tsave, Ks, row0, nvalid);
+    double q = 0.0, m = 0.0;
+    const double* rowp = Ks + (size_t)srow * ldb + spart;
+    for (int k = 0; k < MP; k += 8) {
+      const double v = rowp[k];
+      q = fma(v, v, q);
+      m = fma(sm.beta[spart + k], v, m);
+    }
+    q = fold8(q); m = fold8(m);
+    if (spart == 0) { sm.q1[b][srow] = q; sm.mu[b][srow] = m; }
+    if (a.Tsave) bulk_wait_read();
+    bar_arrive(WS_T_DONE + b, WS_THREADS);
+  };
+  // u of tile i is in its buffer: |u|^2 per row, mean / variance of the tile's rows, bulk store of u; the buffer is free
+  auto finish_u = [&](unsigned i) {
+    const int b = i & 1;
+    const double* Ks = tile_buf(b);
+    const unsigned row0 = tile_of(i) * TR;
+    const int nvalid = (int)min((unsigned)TR, R - row0);
+    bar_sync(WS_U_READY + b, WS_THREADS);
+    if (a.Usave) bulk_rows_out(a.Usave, Ks, row0, nvalid);
+    double q = 0.0;
+    const double* rowp = Ks + (size_t)srow * ldb + spart;
+    for (int k = 0; k < MP; k += 8) { const double v = rowp[k]; q = fma(v, v, q); }
+    q = fold8(q);
+    if (spart == 0 && srow < nvalid) {
+      const double c = sm.kxx[b][srow] - sm.q1[b][srow];
+      const double v = (a.training ? fmax(c, 0.0) : c) + q;
+      a.mu[row0 + srow] = sm.mu[b][srow];
+      a.var[row0 + srow] = v;
+      if (a.craw) a.craw[row0 + srow] = c;
+      if (a.training && c < 0.0 && a.clamp_count) atomicAdd(a.clamp_count, 1u);
+    }
+    if (a.Usave) bulk_wait_read();
+    ssync();      // every support warp is done with the buffer (and the engine has read it)
+  };
+
+  if (n == 0) return;
+  prefetch(0);
+  build(0);
+  for (unsigned i = 0; i < n; ++i) {
+    if (i >= 1) finish_u(i - 1);
+    if (i + 1 < n) build(i + 1);
+    finish_t(i);
+  }
+  finish_u(n - 1);
 }
 
 // Backward through the covariance function for one tile: Ks holds dk = d loss / d K(z_j, row r).  Same thread mapping
@@ -1208,17 +1747,39 @@ static bool first_on_device(bool (&done)[kMaxDevices]) {
 
 int row_grid(long long R) {
   const long long ntiles = (R + TR - 1) / TR;
+#ifdef ROW_TIMING
+  static const int dbg_ctas = getenv("MOBO_ROW_CTAS") ? atoi(getenv("MOBO_ROW_CTAS")) : ROW_CTAS_PER_SM;   // tools/row_bench
+  const long long cap = (long long)num_sms() * dbg_ctas;
+#else
   const long long cap = (long long)num_sms() * ROW_CTAS_PER_SM;
+#endif
   return (int)(ntiles < cap ? (ntiles > 0 ? ntiles : 1) : cap);
 }
 
+static bool g_row_fwd_pingpong = true;      // tools: compare against the two-CTA kernel
 int launch_row_fwd(const RowArgs& a, cudaStream_t st) {
   if (a.MP % 32 != 0 || a.MP > MAX_MP || a.d > kMaxD || a.M > a.MP) return -2;
+  if (a.R >= (1ll << 31) - TR) return -2;      // 32-bit row indices in the kernel; callers chunk (MFDGP.ACQ_CHUNK)
   const size_t smem = row_smem_bytes(a.MP);
   static bool attr_done[kMaxDevices] = {false};
   if (first_on_device(attr_done))
     cudaFuncSetAttribute(row_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes(MAX_MP));
+  static bool attr_done_ws[kMaxDevices] = {false};
+  if (first_on_device(attr_done_ws))
+    cudaFuncSetAttribute(row_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem_bytes(MAX_MP));
   if (a.R <= 0) return 0;
+#ifdef ROW_TIMING
+  g_row_fwd_pingpong = getenv("MOBO_NO_PP") == nullptr;
+#endif
+  if (a.kind == 1 && a.xrep >= XSHARE_MIN_REP && g_row_fwd_pingpong) {
+    // rows are MC samples of few points (S-sample training, acquisition): the warp-specialised kernel, one CTA per SM
+    if ((a.Tsave && ((uintptr_t)a.Tsave & 15)) || (a.Usave && ((uintptr_t)a.Usave & 15))) return -2;   // bulk copies
+    const long long ntiles = (a.R + TR - 1) / TR;
+    const long long grid = ntiles < num_sms() ? ntiles : num_sms();
+    MOBO_LAUNCH("row_fwd_ws_kernel", st,
+                row_fwd_ws_kernel<<<(int)grid, WS_THREADS, ws_smem_bytes(a.MP), st>>>(a));
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
   MOBO_LAUNCH("row_fwd_kernel", st, row_fwd_kernel<<<row_grid(a.R), ROW_THREADS, smem, st>>>(a));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

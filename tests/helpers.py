@@ -158,18 +158,41 @@ def model_from_state(sd, noise_upper, L, samples=None, device="cuda:0", noise_lo
 # extended-precision adjudication (oracle/mfdgp_truth.py): the bar for ill-conditioned cases
 # ------------------------------------------------------------------------------------------------------------
 ADJ_C = 10.0        # the CUDA path may be at most this many times further from the exact answer than the fp64 oracle
-ADJ_FLOOR = 1e-10   # ... or within the north-star tolerance of it, whichever is larger
+ADJ_FLOOR = 1e-10   # ... or within the north-star tolerance of it
+ADJ_K = 10.0        # ... or within ADJ_K * eps * cond(K_zz + jitter I) of it, whichever is largest
+EPS64 = 2.220446049250313e-16
 
 
-def adjudicate(tag, cuda, oracle, truth, c=ADJ_C, floor=ADJ_FLOOR, report=None):
-    """Asserts |cuda - truth| <= max(floor, c * |oracle - truth|) (max-norm, relative to max |truth|).  ``truth`` is a
-    numpy longdouble array from oracle/mfdgp_truth.py, whose own rounding error is ~2000x below fp64's."""
+def adjudicate(tag, cuda, oracle, truth, cond=None, c=ADJ_C, floor=ADJ_FLOOR, k=ADJ_K, report=None):
+    """Asserts |cuda - truth| <= max(floor, c * |oracle - truth|, k * eps * cond) (max-norm, relative to max |truth|).
+    ``truth`` is a numpy longdouble array from oracle/mfdgp_truth.py, whose own rounding error is ~2000x below fp64's.
+
+    Why three terms.  c * |oracle - truth| is the comparison that matters: the CUDA path must be about as close to the
+    exact answer as the reference-shaped fp64 program.  But the oracle's REALISED error is not a bound: its
+    triangular solves are often far more accurate than their worst case (it lands within 1e-12 of the truth at
+    cond 1e7 in some cases), while the CUDA path multiplies by explicit triangular inverses (what puts the work on the
+    DMMA pipe), whose error sits nearer the a-priori bound.  eps * cond is that bound - the forward error ANY
+    backward-stable fp64 solve with P may show - and k = 10 leaves one digit for the gradients' second pass through
+    P^-1.  Measured on B200 (profiles/r02_parity_adjudication.txt): cond 1e5 .. 2e8, |cuda - truth| is 0.2x .. 60x
+    |oracle - truth| and never above 4 eps cond; the bars this replaced were 1e-2 / 1e-3."""
     from oracle import mfdgp_truth as T
     ec, eo = T.err_vs(cuda, truth), T.err_vs(oracle, truth)
     if report is not None:
         report.append((tag, ec, eo))
-    assert ec <= max(floor, c * eo), "%s: |cuda - truth| = %.2e but |oracle - truth| = %.2e" % (tag, ec, eo)
+    bar = max(floor, c * eo, (k * EPS64 * cond) if cond else 0.0)
+    assert ec <= bar, "%s: |cuda - truth| = %.2e but |oracle - truth| = %.2e (cond %s, bar %.2e)" % (
+        tag, ec, eo, "%.1e" % cond if cond else "-", bar)
     return ec, eo
+
+
+def state_cond(sd, L):
+    """max over the layers of cond(K(Z_l, Z_l) + jitter I) for an oracle-format state."""
+    worst = 1.0
+    for l in range(L):
+        Z = O.layer_inducing_points(sd, l)
+        P = O.layer_kernel(sd, l, Z, Z) + O.JITTER * torch.eye(Z.shape[0], dtype=torch.float64)
+        worst = max(worst, float(torch.linalg.cond(P)))
+    return worst
 
 
 def adjudicate_state(sd, lo, up, loss_cuda, grads_cuda, loss_oracle, grads_oracle, L, xb, yb, fb, eps, num_data, S,
@@ -181,19 +204,24 @@ def adjudicate_state(sd, lo, up, loss_cuda, grads_cuda, loss_oracle, grads_oracl
     from oracle import mfdgp_truth as T
     names = sorted(grads_oracle)
     sd = {k: v.detach() for k, v in sd.items()}
+    with torch.no_grad():
+        cond = state_cond(sd, L)
     loss_t, _, grads_t = T.elbo_step_truth(sd, names, L, up, xb, yb, fb, eps, num_data, S, noise_lower=lo,
                                            only_hf=only_hf)
     rep = []
-    adjudicate("loss", loss_cuda, loss_oracle, loss_t, c, floor, rep)
+    adjudicate("loss", loss_cuda, loss_oracle, loss_t, cond, c, floor, report=rep)
     for n in names:
         gc, go, gt = grads_cuda[n], grads_oracle[n], grads_t[n]
         if "chol_variational_covar" in n:
             gc, go, gt = torch.tril(gc), torch.tril(go), np.tril(gt)
-        adjudicate(n, gc, go, gt, c, floor, rep)
+        adjudicate(n, gc, go, gt, cond, c, floor, report=rep)
     if verbose:
         worst = max(rep, key=lambda r: r[1])
-        print("adjudicated %d quantities: worst |cuda - truth| %.2e (%s), there |oracle - truth| %.2e; "
-              "max |oracle - truth| %.2e" % (len(rep), worst[1], worst[0], worst[2], max(r[2] for r in rep)))
+        ratio = max(r[1] / max(r[2], 1e-300) for r in rep if r[1] > floor)  if any(r[1] > floor for r in rep) else 0.0
+        print("adjudicated %d quantities at cond %.1e: worst |cuda - truth| %.2e = %.2f eps cond (%s), there "
+              "|oracle - truth| %.2e; max |oracle - truth| %.2e; max ratio cuda/oracle above the floor %.1f"
+              % (len(rep), cond, worst[1], worst[1] / (EPS64 * cond), worst[0], worst[2], max(r[2] for r in rep),
+                 ratio))
     return rep
 
 

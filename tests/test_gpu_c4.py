@@ -63,9 +63,10 @@ def test_c4_exact_config_well_conditioned():
     worst, where = _worst_grad(grads, grads_o)
     print("C4 (l = 0.3): cond %.2e  tol %.1e  loss relerr %.2e  KL relerr %.2e  worst grad relerr %.2e (%s)"
           % (cond, tol, relerr(loss, loss_o), relerr(kl, kl_o), worst, where))
-    assert cond < 1e5
-    assert relerr(loss, loss_o) < tol and relerr(kl, kl_o) < tol
-    assert worst < 1e3 * tol, (where, worst)
+    # cond(K_zz + jitter I) is 6e5 here (the upper layers' k_x1 has lengthscale 10 l): the cond * eps bar would be
+    # 2.7e-9, but the north star's flat 1e-10 holds for the values, and 1e-9 for every gradient
+    assert relerr(loss, loss_o) < 1e-10 and relerr(kl, kl_o) < 1e-10
+    assert worst < 1e-9, (where, worst)
 
 
 def test_c4_exact_config_reference_default_lengthscale():

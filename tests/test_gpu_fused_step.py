@@ -109,7 +109,9 @@ def test_fused_step_matches_oracle_and_composable(L, S, B, M, freeze):
             step(xb[a:b], yb[a:b], fb[a:b], eps=e, num_samples=S)
             acc += step.flat.flat
         # every shard carries the KL term scaled by its own B_r / N: they add up to the full step's B / N
-        assert relerr(acc, full) < 1e-10, relerr(acc, full)
+        # (the SYRK partials fold in another order per partition: ~1e-16 sqrt(rows) there, times cond through
+        # dP = W^T N W; an indexing slip in the multi-tile pipelines is an O(1) error)
+        assert relerr(acc, full) < tol, (relerr(acc, full), tol)
     for n in names:
         gf, go = g_fused[n], sd[n].grad
         if "chol_variational_covar" in n:
