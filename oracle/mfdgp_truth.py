@@ -230,6 +230,58 @@ def elbo_step_truth(sd_torch, names, L, noise_upper, x, y, fid, eps, num_data, S
     return loss.v, kl.v, grads
 
 
+class covariance_rounding(object):
+    """Context manager: every covariance matrix the truth evaluates inside it is multiplied element by element by
+    (1 + eps64 * xi), xi uniform in [-1, 1] (seeded; K(Z_l, Z_l) symmetrically and with the same draw wherever it is
+    used).  The change of a result under it is that result's sensitivity to ROUNDING THE COVARIANCE ENTRIES TO fp64 -
+    the forward error an fp64 program that forms K may show however carefully it then solves with it.  Unlike
+    eps * cond(K_zz) it is specific to each quantity: a gradient that is a small difference of large terms (layer 0's
+    outputscale at the reference's default initialisation: every term depends on it only through jitter / a) has a large
+    one."""
+
+    def __init__(self, seed, scale=2.220446049250313e-16):
+        self.rng, self.scale, self.zz = np.random.default_rng(seed), scale, {}
+
+    def __enter__(self):
+        global layer_kernel
+        self.orig = layer_kernel
+
+        def noisy(sd, l, Xa, Xb):
+            K = self.orig(sd, l, Xa, Xb)
+            if Xa is Xb:
+                if l not in self.zz:
+                    xi = self.rng.uniform(-1.0, 1.0, size=K.shape)
+                    self.zz[l] = np.triu(xi) + np.triu(xi, 1).T
+                xi = self.zz[l]
+            else:
+                xi = self.rng.uniform(-1.0, 1.0, size=K.shape)
+            return K * (LD(1) + LD(self.scale) * xi.astype(LD))
+        layer_kernel = noisy
+        return self
+
+    def __exit__(self, *exc):
+        global layer_kernel
+        layer_kernel = self.orig
+        return False
+
+
+def elbo_step_rounding_sensitivity(sd_torch, names, L, noise_upper, x, y, fid, eps, num_data, S, truth, draws=6,
+                                   noise_lower=NOISE_LOWER, only_hf=False):
+    """{name or "loss": max over ``draws`` of max |truth(perturbed K) - truth| / max |truth|}; truth = (loss, grads) as
+    returned by ``elbo_step_truth`` on the same arguments."""
+    loss_t, grads_t = truth
+    out = {n: 0.0 for n in list(names) + ["loss"]}
+    for k in range(draws):
+        with covariance_rounding(1000 + k):
+            loss_p, _, grads_p = elbo_step_truth(sd_torch, names, L, noise_upper, x, y, fid, eps, num_data, S,
+                                                 noise_lower=noise_lower, only_hf=only_hf)
+        out["loss"] = max(out["loss"], float(abs(loss_p - loss_t) / abs(loss_t)))
+        for n in names:
+            den = np.max(np.abs(grads_t[n]))
+            out[n] = max(out[n], float(np.max(np.abs(grads_p[n] - grads_t[n])) / (den if den > 0 else LD(1))))
+    return out
+
+
 def jes_truth(mod_u, mod_c, X, fidelity):
     """(jes values (n,), d sum(jes) / dX (n, d)) for one black box; mod_* as in the oracle's ``jes_mfdgp``."""
     Xn = A.leaf(X.reshape(-1, X.shape[-1]))

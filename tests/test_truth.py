@@ -94,3 +94,28 @@ def test_truth_adjudicates_ill_conditioned_case():
     print("cond %.1e  loss err %.1e  worst grad err of the fp64 oracle %.1e" % (cond, T.err_vs(loss_o, loss_t), worst))
     assert T.err_vs(loss_o, loss_t) < 1e-6 and worst < 1e-2      # the oracle is a correct fp64 program ...
     assert worst > 1e-13                                          # ... whose rounding error the truth resolves
+
+
+def test_covariance_rounding_sensitivity():
+    """The third term of the adjudication bar (tests/helpers.adjudicate): how far the truth moves when every covariance
+    entry is rounded like an fp64 program rounds it.  It must be a rounding-sized effect (far below the old 1e-3 bars),
+    scale with the perturbation, and leave the module as it found it."""
+    L, S, B = 2, 2, 30
+    sd, up, x, y, fid, eps = _case(40, 2, L, B, S, ls=0.9)
+    names = param_keys(sd)
+    before = T.layer_kernel
+    loss_t, _, grads = T.elbo_step_truth(sd, names, L, up, x, y, fid, eps, 3 * B, S)
+    sens = T.elbo_step_rounding_sensitivity(sd, names, L, up, x, y, fid, eps, 3 * B, S, (loss_t, grads), draws=2)
+    assert T.layer_kernel is before
+    Z = O.layer_inducing_points(sd, 0)
+    cond = float(torch.linalg.cond(O.layer_kernel(sd, 0, Z, Z) + 1e-6 * torch.eye(40, dtype=torch.float64)))
+    worst = max(sens.values())
+    print("cond %.1e: covariance-rounding sensitivity of the loss %.1e, worst gradient %.1e" % (cond, sens["loss"], worst))
+    assert all(v > 0.0 for v in sens.values())
+    assert sens["loss"] < 2.3e-16 * cond and worst < 1e-6
+    with T.covariance_rounding(1000, scale=2.220446049250313e-13):
+        loss_p, _, _ = T.elbo_step_truth(sd, names, L, up, x, y, fid, eps, 3 * B, S)
+    with T.covariance_rounding(1000):
+        loss_q, _, _ = T.elbo_step_truth(sd, names, L, up, x, y, fid, eps, 3 * B, S)
+    ratio = float(abs(loss_p - loss_t) / abs(loss_q - loss_t))
+    assert 500 < ratio < 2000, ratio       # linear in the perturbation: a sensitivity, not noise
