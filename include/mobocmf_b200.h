@@ -4,7 +4,10 @@
  * entry points are what a binding for that path would call; each cites the reference code it replaces.  All
  * pointers are DEVICE pointers to fp64 unless stated; sizes are explicit; `stream` is a cudaStream_t passed as
  * void*.  Every function returns 0 on success, -1 on a CUDA launch error, -2 on an unsupported shape
- * (M > 256, d > 8).  No function synchronises, allocates or keeps global state; scratch is caller-provided.
+ * (M > 256, d > 8).  No function synchronises or allocates device memory; scratch is caller-provided.  State kept by
+ * the library: launch counters / the optional profile log, and the side stream + events of the fused step, which live
+ * in a caller-owned step context (mobo_step_ctx_create) or, for callers that pass none, in one lazily created
+ * per-device default.
  *
  * Conventions
  *   kind 0  layer-0 covariance  a * RBF_ARD(x)                       (mobocmf/layers/mfdgp_hidden_layer.py:43-47)
@@ -29,7 +32,7 @@
 extern "C" {
 #endif
 
-/* library / build identification: 101 (sm_100a; 100 + ABI revision) */
+/* library / build identification: 102 (sm_100a; 100 + ABI revision; 2: mobo_step_desc.ctx, step contexts) */
 int mobo_abi_version(void);
 
 /* Launch accounting: number of kernels this library has launched in this process; optional per-launch CUDA-event
@@ -149,11 +152,18 @@ typedef struct mobo_step_desc {
                                                   (pass &out[6] to mobo_adam as skip_flag); [7] retries used (0..3)  */
   double* workspace;                           /* mobo_elbo_step_workspace_doubles(...) doubles                  */
   int accumulate;                              /* 0: gradients are overwritten, 1: added to                      */
+  void* ctx;                                   /* mobo_step_ctx_create() handle (side stream + events of this caller) or
+                                                  NULL: the per-device default context                              */
 } mobo_step_desc;
 
 size_t mobo_elbo_step_workspace_doubles(int L, int d, int M, int S, long long B);
-/* mobo_elbo_step runs each layer's operator-chain backward on an internal side stream behind the row kernels
- * (default).  0 serialises everything on the caller's stream (used by bench.py's per-kernel timing leg). */
+/* Step context: the side stream (non-blocking, on the current device) and the fork / join events with which
+ * mobo_elbo_step runs each layer's operator-chain backward behind the row kernels.  One per concurrently stepping
+ * caller (models trained on different streams must not share one: their side work would serialise); destroy it after
+ * the last step that used it has completed.  Returns NULL on a CUDA error. */
+void* mobo_step_ctx_create(void);
+void mobo_step_ctx_destroy(void* ctx);
+/* 0 serialises everything on the caller's stream (used by bench.py's per-kernel timing leg); default 1. */
 void mobo_step_side_stream(int on);
 int mobo_elbo_step(const mobo_step_desc* desc, void* stream);
 

@@ -103,17 +103,24 @@ class JESMOC_MFDGP():
             acq = add(acq, con(X.double()))
         return acq
 
-    def _optimize(self, fidelity):
-        from ..util.optimize import optimize_acqf
-        return optimize_acqf(acq_function=lambda x: self.coupled_acq(x, fidelity=fidelity),
-                             bounds=self.standard_bounds, q=1, num_restarts=5, raw_samples=200,
-                             options={"maxiter": 200})
+    def _optimize(self, fidelities):
+        """optimize_acqf (acquisition_functions/JESMOC_MFDGP.py:142-143,159-160) of the coupled acquisition of every
+        fidelity in ``fidelities`` in ONE multi-start run: all restarts of all fidelities form one batch per L-BFGS
+        iteration, whose value-and-gradient evaluation is replayed from a CUDA graph (util/optimize.py)."""
+        from ..util.optimize import optimize_acqf_multi
+        fns = [(lambda x, f=f: self.coupled_acq(x, fidelity=f)) for f in fidelities]
+        out, self.last_optimize_info = optimize_acqf_multi(fns, bounds=self.standard_bounds, q=1, num_restarts=5,
+                                                           raw_samples=200, options={"maxiter": 200},
+                                                           return_info=True)
+        from .. import functional
+        functional.check_status()       # a failed operator chain during the run surfaces here (one synchronisation)
+        return out
 
     def _get_nextpoint_coupled_highest_fidelity(self, iteration=None, verbose=False):
         if verbose:
             assert (iteration is not None)
         fidelity_to_evaluate = self.num_fidelities - 1
-        current_candidate, current_value = self._optimize(self.num_fidelities - 1)
+        (current_candidate, current_value), = self._optimize([self.num_fidelities - 1])
         current_value_weighted = current_value / self.costs_blackboxes[0]["total"]
         nextpoint = current_candidate[0, :]
         if verbose:
@@ -125,8 +132,8 @@ class JESMOC_MFDGP():
         if verbose:
             assert (iteration is not None)
         current_value_weighted = 0.0
-        for fidelity in range(self.num_fidelities):
-            new_candidate, new_values = self._optimize(fidelity)
+        results = self._optimize(list(range(self.num_fidelities)))      # the reference loops over the fidelities
+        for fidelity, (new_candidate, new_values) in enumerate(results):
             new_values_weighted = new_values / self.costs_blackboxes[fidelity]["total"]
             if (fidelity == 0) or (current_value_weighted < new_values_weighted):
                 fidelity_to_evaluate = fidelity

@@ -1,6 +1,7 @@
 // extern "C" entry points of libmobocmf_b200.so (declared in include/mobocmf_b200.h) and the host-side kernel
 // sequences behind them.
 #include <string.h>
+#include <mutex>
 #include "../../include/mobocmf_b200.h"
 #include "matrix_ops.cu"
 #include "opchain.cu"
@@ -15,7 +16,7 @@ static inline int padded(int M) { return ((M + 31) / 32) * 32; }
 
 extern "C" {
 
-int mobo_abi_version(void) { return 101; }
+int mobo_abi_version(void) { return 102; }
 
 long long mobo_launch_count(void) { return prof_state().launches; }
 
@@ -53,7 +54,7 @@ size_t mobo_rows_save_doubles(int M, long long R) {
 
 size_t mobo_rows_bwd_work_doubles(int M, long long R) {
   const int MP = padded(M);
-  return (size_t)256 * KG_CTAS_PER_SM * (MAX_THETA + MP) + syrk_part_doubles(MP, R) + (size_t)syrk_nchunk(MP, R) * MP + 64 +
+  return (size_t)256 * KG_CTAS_PER_SM * (MAX_THETA + MP) + syrk_part_doubles(MP, R) + syrk_alpha_doubles(MP, syrk_nchunk(MP, R)) + 64 +
          mobo_rows_save_doubles(M, R);   // + the dk scratch [R][MP]
 }
 
@@ -376,7 +377,7 @@ StepLayout step_layout(int L, int d, int M, int S, long long B) {
     // in the next layer's SYRK
     y.stats0[l] = take(syrk_part_doubles(MP, R));
     y.stats1[l] = take(syrk_part_doubles(MP, R));
-    y.stats_alpha[l] = take((size_t)syrk_nchunk(MP, R) * MP + 64);
+    y.stats_alpha[l] = take(syrk_alpha_doubles(MP, syrk_nchunk(MP, R)) + 64);
   }
   y.rows_work = take(rows_work);
   y.total = off;
@@ -386,25 +387,46 @@ StepLayout step_layout(int L, int d, int M, int S, long long B) {
 
 }  // namespace
 
-// Side stream of the fused step (one per device, created on first use): the SYRK statistics and the operator-chain
-// backward of layer l run there while the main stream already works on layer l - 1's row kernels; forked and joined
-// with events inside mobo_elbo_step, so the pattern is also valid under CUDA-graph capture.
+// Side stream of the fused step: the fold of the SYRK partials and the operator-chain backward of layer l run there
+// while the main stream already works on layer l - 1's row kernels; forked and joined with events inside
+// mobo_elbo_step, so the pattern is also valid under CUDA-graph capture.  The stream and its events belong to a step
+// context the caller creates (mobo_step_ctx_create: one per concurrently trained model, so that independent models do
+// not serialise on each other's side stream); a step without a context uses one per-device default, created under a
+// lock on first use - the only state this library keeps.
 namespace {
-struct SideCtx { bool init = false; cudaStream_t s = nullptr; cudaEvent_t fork[ST_MAX_LAYERS]; cudaEvent_t join = nullptr; };
-SideCtx& side_ctx() {
+struct SideCtx { int device = -1; cudaStream_t s = nullptr; cudaEvent_t fork[ST_MAX_LAYERS]; cudaEvent_t join = nullptr; };
+bool side_ctx_init(SideCtx& c) {
+  if (cudaGetDevice(&c.device) != cudaSuccess) return false;
+  if (cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking) != cudaSuccess) return false;
+  for (int i = 0; i < ST_MAX_LAYERS; ++i)
+    if (cudaEventCreateWithFlags(&c.fork[i], cudaEventDisableTiming) != cudaSuccess) return false;
+  return cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) == cudaSuccess;
+}
+SideCtx* default_side_ctx() {
   static SideCtx ctx[64];
+  static std::mutex mu;
   int dev = 0;
-  cudaGetDevice(&dev);
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
   SideCtx& c = ctx[dev & 63];
-  if (!c.init) {
-    cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking);
-    for (int i = 0; i < ST_MAX_LAYERS; ++i) cudaEventCreateWithFlags(&c.fork[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming);
-    c.init = true;
-  }
-  return c;
+  if (c.device < 0 && !side_ctx_init(c)) return nullptr;
+  return &c;
 }
 }  // namespace
+
+void* mobo_step_ctx_create(void) {
+  SideCtx* c = new SideCtx();
+  if (!side_ctx_init(*c)) { delete c; return nullptr; }
+  return c;
+}
+void mobo_step_ctx_destroy(void* ctx) {
+  SideCtx* c = static_cast<SideCtx*>(ctx);
+  if (!c) return;
+  if (c->s) cudaStreamDestroy(c->s);
+  for (int i = 0; i < ST_MAX_LAYERS; ++i) if (c->fork[i]) cudaEventDestroy(c->fork[i]);
+  if (c->join) cudaEventDestroy(c->join);
+  delete c;
+}
 
 static bool g_side_stream_on = true;
 // SMs the backward product kernel (one persistent CTA per SM, all of its registers and shared memory) leaves to the
@@ -473,8 +495,10 @@ int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
   // 4. ELBO terms and backward row passes, high -> low fidelity.  Per layer the main stream runs the SYRK statistics,
   //    the product and the covariance-gradient kernels; that layer's operator-chain backward (a dozen latency-bound
   //    M x M launches) runs on the side stream, hidden behind the row kernels.
-  SideCtx& sc = side_ctx();
-  const bool fork = g_side_stream_on;
+  SideCtx* scp = D->ctx ? static_cast<SideCtx*>(D->ctx) : (g_side_stream_on ? default_side_ctx() : nullptr);
+  const bool fork = g_side_stream_on && scp != nullptr;
+  SideCtx dummy;
+  SideCtx& sc = scp ? *scp : dummy;
   cudaStream_t ss = fork ? sc.s : st;
   for (int l = L - 1; l >= 0; --l) {
     const long long R = y.R[l];

@@ -23,13 +23,19 @@ namespace mobo {
 // ---- optional per-phase cycle accounting of the row kernels (tools/row_bench.cu builds with -DROW_TIMING) ----
 #ifdef ROW_TIMING
 __device__ unsigned long long row_times[3][512][16];
-#define RT_DECL __shared__ unsigned long long rt_acc[16]; unsigned long long rt_prev = clock64(); \
-  if (threadIdx.x == 0) for (int k_ = 0; k_ < 16; ++k_) rt_acc[k_] = 0ull;
-#define RT_TICK(k) do { if (threadIdx.x == 0) { const unsigned long long n_ = clock64(); rt_acc[k] += n_ - rt_prev; rt_prev = n_; } } while (0)
-#define RT_FLUSH(which) do { if (threadIdx.x == 0 && blockIdx.x < 512) for (int k_ = 0; k_ < 16; ++k_) row_times[which][blockIdx.x][k_] = rt_acc[k_]; } while (0)
+// RT_DECL: thread 0 of the CTA keeps the clock; RT_DECL_ROLE(cond): the thread for which cond holds (one per role of the
+// warp-specialised kernel, each with its own accumulators in shared memory)
+#define RT_DECL_ROLE(cond) __shared__ unsigned long long rt_acc_[3][16]; const bool rt_me = (cond); unsigned long long rt_prev = clock64(); \
+  if (threadIdx.x < 48) rt_acc_[threadIdx.x / 16][threadIdx.x % 16] = 0ull;
+#define RT_DECL RT_DECL_ROLE(threadIdx.x == 0)
+#define RT_TICKW(w, k) do { if (rt_me) { const unsigned long long n_ = clock64(); rt_acc_[w][k] += n_ - rt_prev; rt_prev = n_; } } while (0)
+#define RT_TICK(k) RT_TICKW(0, k)
+#define RT_FLUSH(which) do { if (rt_me && blockIdx.x < 512) for (int k_ = 0; k_ < 16; ++k_) row_times[which][blockIdx.x][k_] = rt_acc_[which][k_]; } while (0)
 #else
 #define RT_DECL
+#define RT_DECL_ROLE(cond)
 #define RT_TICK(k)
+#define RT_TICKW(w, k)
 #define RT_FLUSH(which)
 #endif
 
@@ -92,25 +98,31 @@ struct KernFast {
 };
 
 constexpr double kExp2Magic = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to the nearest integer
-constexpr int kExp2TabBits = 6, kExp2Tab = 1 << kExp2TabBits;
+constexpr int kExp2TabBits = 8, kExp2Tab = 1 << kExp2TabBits;
 
-// 2^y for y <= ~1000 to ~1.5 ulp: y = n / 64 + r, |r| <= 1/128; 2^y = 2^(n >> 6) * tab[n & 63] * p5(r).
-// 10 FP64-pipe operations against ~22 for libdevice exp(); the row kernels evaluate 3 of these per (row, inducing
-// point) pair, and DFMA shares the FP64 pipe with the DMMA products (profiles/r01c_fp64_probe_*.log).
+// 2^y to ~1.5 ulp: y = n / 256 + r, |r| <= 1/512; 2^y = 2^(n >> 8) * tab[n & 255] * p4(r) (truncation 3.8e-17).
+// 8 FP64-pipe operations against ~22 for libdevice exp(): the row kernels evaluate up to 3 of these per (row, inducing
+// point) pair, DFMA shares the FP64 pipe with the DMMA products (profiles/r01c_fp64_probe_*.log), and next to warps
+// that stream DMMAs every FP64 instruction of another warp waits for an arbitration slot (row_fwd_ws_kernel), so the
+// count matters more than the pipe time: the clamp is done on the integer pipe (arguments below -1000 give 0 for every
+// purpose here; they are never NaN), and a 256-entry table buys one polynomial degree.
 __device__ __forceinline__ double exp2_tab(double y, const double* __restrict__ tab) {
-  y = fmax(y, -1000.0);                                 // below this the result is 0 for every purpose here
+  // y < -1000 (sign bit set, magnitude above 1000.0 = 0x408F4000_00000000): clamp, comparing the high word as unsigned
+  if ((unsigned)__double2hiint(y) > 0xC08F4000u) y = -1000.0;
   const double t = fma(y, (double)kExp2Tab, kExp2Magic);
   const int n = __double2loint(t);
   const double nf = t - kExp2Magic;
   const double r = fma(nf, -1.0 / kExp2Tab, y);         // exact
-  double p = 1.3333558146428443e-3;                      // ln2^5 / 5!
-  p = fma(p, r, 9.618129107628477e-3);                   // ln2^4 / 4!
+  double p = 9.618129107628477e-3;                       // ln2^4 / 4!
   p = fma(p, r, 5.550410866482158e-2);                   // ln2^3 / 3!
   p = fma(p, r, 2.402265069591007e-1);                   // ln2^2 / 2!
   p = fma(p, r, 6.931471805599453e-1);                   // ln2
   p = fma(p, r, 1.0);
   const double res = tab[n & (kExp2Tab - 1)] * p;
   return __hiloint2double(__double2hiint(res) + ((n >> kExp2TabBits) << 20), __double2loint(res));
+}
+__device__ __forceinline__ void fill_exp2_tab(double* tab, int tid, int nthreads) {
+  for (int i = tid; i < kExp2Tab; i += nthreads) tab[i] = exp2((double)i / kExp2Tab);
 }
 
 constexpr int RPW = 4;   // tile rows per warp in the covariance phases (independent exponent chains per thread)
@@ -338,7 +350,7 @@ template <class SM>
 __device__ __forceinline__ void load_inducing(const RowArgs& a, SM& sm, bool with_zx = true) {
   const int tid = threadIdx.x;
   if (tid == 0) load_kern_fast(sm.kf, a.kind, a.d, a.theta);
-  if (tid >= 32 && tid < 32 + kExp2Tab) sm.e2tab[tid - 32] = exp2((double)(tid - 32) / kExp2Tab);
+  fill_exp2_tab(sm.e2tab, tid, SM::THREADS);
   if (with_zx)
     for (int idx = tid; idx < a.MP * a.d; idx += SM::THREADS) {
       const int j = idx / a.d, c = idx - j * a.d;
@@ -777,35 +789,56 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_CTAS_PER_SM) row_fwd_kernel(c
 // S-sample training tiles and the acquisition tiles; `xshare`).
 //
 // What the measurements said (tools/row_bench -DROW_TIMING, profiles/r02_row_fwd_phases.txt):
-//  * DFMA and DMMA share the FP64 pipe and the schedulers arbitrate between warps, not work: next to a warp that
-//    streams DMMAs (16 pipe cycles each) a covariance-build warp gets ONE FP64 instruction through per 36 - 72 cycles.
-//    With two co-resident CTAs the build was 23 - 30 % of a CTA's time and the pipe idled 26 % of the time - whenever
-//    both CTAs were outside their products at once (their phases drift freely).
-//  * a ping-pong of two 8-warp groups with a pipe token did not help: the group outside the token (building) is starved
-//    so thoroughly that it is not ready when the token comes back.
+//  * DFMA and DMMA share the FP64 pipe and the schedulers arbitrate between warps, not work: next to warps that stream
+//    DMMAs (16 pipe cycles each) every FP64 instruction of another warp waits 60 - 700 cycles for its turn, however
+//    little of the pipe its 2-cycle DFMAs need and whatever else that warp has in flight (4 independent exponent chains
+//    per thread ran no faster than 1).  With two co-resident CTAs the build was 23 - 30 % of a CTA's time and the pipe
+//    idled 26 % of the time - whenever both CTAs were outside their products at once.
 //  * a lone CTA's products run at 89 % of the pipe.
-// So: ONE CTA per SM, 8 PRODUCT warps that do nothing but the two triangular DMMA products tile after tile (plus the
-// accumulator -> shared-memory hand-overs), and 8 SUPPORT warps that do everything else one tile ahead / behind, out
-// of the products' way - starved, but with a whole tile period for half a period of work:
-//     support:  rows (prefetched), K(Z, rows) of tile i+1 into the other tile buffer | row sums of t(i), bulk store
-//               of t(i) | row sums of u(i-1), bulk store of u(i-1), mean / variance of tile i-1
-//     product:  t = W k | t -> tile (in place of K) | u = H^T t | u -> tile (in place of t)
-// Two tile buffers, each cycling K -> t -> u; eight named barriers hand them over (arrive by the producer group, sync
-// by the consumer group).  The row sums |t|^2, beta.t, |u|^2 are taken from shared memory by the support warps (the
-// first version reduced them from the accumulators with 48 shuffles per thread inside the product warps), and u leaves
-// as one bulk copy per row like t (it used to be 32 scattered 8-byte stores per thread).
+//  * 8 product + 8 support warps doing build / row sums / stores in sequence: the product warps waited 16 % of the time
+//    for the support group (~4700 FP64 warp-instructions per tile, ~600 per warp).
+// So: ONE CTA per SM and three roles; `setmaxnreg` moves the registers to the product warps:
+//   8 PRODUCT warps (128 registers): nothing but the two triangular DMMA products, tile after tile, and the accumulator
+//     -> shared-memory hand-overs:  t = W k | t -> tile (in place of K) | u = H^T t | u -> tile (in place of t)
+//   16 BUILD warps (48 registers), the covariance build spread evenly over them, in two stages one tile apart so that
+//     no warp waits for another inside a stage:  K(Z, rows of tile i) from the x-kernel values (2 rows per warp), THEN
+//     - off the path the product warps wait on - the x-kernel values and row data of tile i + 1
+//   4 FINISH warps (48 registers): |t|^2, beta.t and the bulk store of t as soon as t is in the buffer (this is what the
+//     product warps wait for before u may replace t); then |u|^2, bulk store of u, mean / variance; buffer released
+// Two tile buffers, each cycling K -> t -> u; ten named barriers hand them over (arrive by the producer role, sync by
+// the consumer role).  The row sums are taken from shared memory (the first kernel reduced them from the accumulators
+// with 48 shuffles per thread inside the product warps), and t / u leave as one bulk (TMA engine) copy per row.
+// Tried on top of this and measured, not kept (all within 0.65 - 0.69 of the DMMA peak; the support side's FP64
+// instructions get through at ~1 per 40 cycles and scheduler whatever their organisation, and that rate, not the
+// dependencies, sets the tile time once the products themselves are down to 41k cycles): row sums pre-reduced by the
+// product warps from their accumulators (what the finish warps saved the product warps lost in their hand-overs); 16
+// symmetric support warps that own two rows of every tile for build, sums and stores; the product warps building a
+// quarter of K themselves between two tiles.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int WS_THREADS = 2 * ROW_THREADS;
+constexpr int WS_PROD_WARPS = ROW_WARPS, WS_BUILD_WARPS = 16, WS_FIN_WARPS = 4;
+constexpr int WS_PROD_THREADS = WS_PROD_WARPS * 32, WS_BUILD_THREADS = WS_BUILD_WARPS * 32, WS_FIN_THREADS = WS_FIN_WARPS * 32;
+constexpr int WS_THREADS = WS_PROD_THREADS + WS_BUILD_THREADS + WS_FIN_THREADS;      // 896: launched with 72 registers
+// 8 x 32 x 128 + 20 x 32 x 48 = 63488 <= 896 x 72 = 64512 (an exact fit of the whole file, tried as 128 + 64 with 24
+// warps, never gets its registers: the kernel hangs in setmaxnreg.inc)
+constexpr int WS_PROD_REGS = 128, WS_SUPPORT_REGS = 48;
+constexpr int WS_ROWS_PER_WARP = TR / WS_BUILD_WARPS;       // K build: tile rows per build warp
+static_assert(WS_PROD_WARPS % 4 == 0 && WS_BUILD_WARPS % 4 == 0 && WS_FIN_WARPS % 4 == 0, "setmaxnreg is per warpgroup");
+static_assert(WS_ROWS_PER_WARP * WS_BUILD_WARPS == TR && WS_BUILD_THREADS == 2 * MAX_MP && XMAX == 4, "build thread mapping");
+// per-tile scratch of the build role, double-buffered: stage 1 fills tile i + 1's after stage 2 has read tile i's
+struct WsScratch {
+  double fs[TR], vfs[TR];                       // propagated input f of the tile's rows, v_lin f
+  int xsel[TR];                                 // which of the tile's distinct x a row reads
+  double s12[2 * XMAX][MAX_MP];                 // [0, XMAX): a1 E1(x_c, z_j);  [XMAX, 2 XMAX): a2 E2(x_c, z_j)
+};
 struct WsSmem {
   KernFast kf;
   double e2tab[kExp2Tab];
   double zfs[MAX_MP];
   double beta[MAX_MP];
-  double fs[TR];
-  int xsel[TR];
-  double xs[XMAX][kMaxD];
-  double kxx[2][TR], q1[2][TR], mu[2][TR];     // per tile buffer
-  double s12[2 * XMAX][MAX_MP];                 // [0, XMAX): a1 E1(x_c, z_j);  [XMAX, 2 XMAX): a2 E2(x_c, z_j)
+  double zsT[kMaxD][MAX_MP];                    // Z^T (x part of the inducing inputs)
+  double kxx[4][TR];                            // per tile, slot i & 3 (written a tile before the finish warps read it)
+  double q1[2][TR], mu[2][TR];                  // per tile buffer
+  WsScratch scr[2];
 };
 __host__ __device__ inline size_t ws_head_bytes() { return ((sizeof(WsSmem) + 127) / 128) * 128; }
 __host__ inline size_t ws_smem_bytes(int MP) {
@@ -813,37 +846,48 @@ __host__ inline size_t ws_smem_bytes(int MP) {
 }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-// named barriers: 1 product group, 2 support group, then per tile buffer b (0 / 1):
-constexpr int WS_BAR_PROD = 1, WS_BAR_SUPP = 2;
-constexpr int WS_K_READY = 3;    // + b  support -> product: K(Z, rows) is in the buffer
-constexpr int WS_T_READY = 5;    // + b  product -> support: t has replaced K
-constexpr int WS_T_DONE = 7;     // + b  support -> product: t's row sums and bulk store are done, u may replace it
-constexpr int WS_U_READY = 9;    // + b  product -> support: u has replaced t
+// named barriers: one per role, then per tile buffer b (0 / 1):
+constexpr int WS_BAR_PROD = 1, WS_BAR_BUILD = 2;
+constexpr int WS_K_READY = 4;    // + b  build -> product:  K(Z, rows) is in the buffer
+constexpr int WS_T_READY = 6;    // + b  product -> finish: t has replaced K
+constexpr int WS_T_DONE = 8;     // + b  finish -> product: t's row sums and bulk store are done, u may replace it
+constexpr int WS_U_READY = 10;   // + b  product -> finish: u has replaced t
+constexpr int WS_BUF_FREE = 12;  // + b  finish -> build:   u's row sums and bulk store are done, the buffer is free
+constexpr int WS_N_K = WS_BUILD_THREADS + WS_PROD_THREADS, WS_N_PF = WS_PROD_THREADS + WS_FIN_THREADS,
+              WS_N_FB = WS_FIN_THREADS + WS_BUILD_THREADS;
 
 __global__ void __launch_bounds__(WS_THREADS, 1) row_fwd_ws_kernel(const __grid_constant__ RowArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_raw);
   const int MP = a.MP, ldb = MP + 4;
-  const bool support = threadIdx.x >= ROW_THREADS;
-  const int tid = threadIdx.x & (ROW_THREADS - 1), lane = tid & 31, warp = tid >> 5;
+  const int role = threadIdx.x < WS_PROD_THREADS ? 0 : (threadIdx.x < WS_PROD_THREADS + WS_BUILD_THREADS ? 1 : 2);
+  const int tid = role == 0 ? threadIdx.x : (role == 1 ? threadIdx.x - WS_PROD_THREADS
+                                                        : threadIdx.x - WS_PROD_THREADS - WS_BUILD_THREADS);
+  const int lane = tid & 31, warp = tid >> 5;
   double* tiles = reinterpret_cast<double*>(smem_raw + ws_head_bytes());
   auto tile_buf = [&](int b) { return tiles + (size_t)b * (tile_bytes(MP) / sizeof(double)); };
   const unsigned R = (unsigned)a.R, ntiles = (R + TR - 1) / TR;
   const unsigned n = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;   // this CTA's tiles
+  auto tile_of = [&](unsigned i) { return blockIdx.x + i * gridDim.x; };
 
-  RT_DECL
-  // ---- data shared by both groups ----
+  RT_DECL_ROLE(tid == 0)
+  // ---- data shared by the roles ----
   if (threadIdx.x == 0) load_kern_fast(sm.kf, a.kind, a.d, a.theta);
-  if (threadIdx.x >= 32 && threadIdx.x < 32 + kExp2Tab) sm.e2tab[threadIdx.x - 32] = exp2((double)(threadIdx.x - 32) / kExp2Tab);
+  fill_exp2_tab(sm.e2tab, threadIdx.x, WS_THREADS);
   for (int j = threadIdx.x; j < MP; j += WS_THREADS) {
     sm.zfs[j] = j < a.M ? a.zf[j] : 0.0;
     sm.beta[j] = (a.ops + ops_beta(MP))[j];
   }
+  for (int idx = threadIdx.x; idx < MP * a.d; idx += WS_THREADS) {
+    const int j = idx / a.d, c = idx - j * a.d;
+    sm.zsT[c][j] = j < a.M ? a.Zx[(size_t)j * a.d + c] : 0.0;
+  }
   __syncthreads();
   RT_TICK(0);
 
-  if (!support) {
+  if (role == 0) {
     // =========================== product warps ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_PROD_REGS));
     double2* ring = reinterpret_cast<double2*>(smem_raw + ws_head_bytes() + 2 * tile_bytes(MP)) + warp * FWD_NST * 32;
     const int p = warp, npairs = MP / 32, ns = MP / 16;
     const bool active = p < npairs;
@@ -859,7 +903,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) row_fwd_ws_kernel(const __grid_
       const int b = i & 1;
       double* Ks = tile_buf(b);
       double acc[2][2][4][2];
-      bar_sync(WS_K_READY + b, WS_THREADS);
+      bar_sync(WS_K_READY + b, WS_N_K);
       RT_TICK(1);
       // ---- t = W k ----
       zero_acc(acc);
@@ -868,11 +912,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) row_fwd_ws_kernel(const __grid_
         frag_segment<false>(acc[1], W, MP, Ks, ldb, sB, 0, lane, ring, frag_start(G, MP, sA, true, lane));
       }
       RT_TICK(2);
-      bar_sync(WS_BAR_PROD, ROW_THREADS);   // every product warp is done reading K
+      bar_sync(WS_BAR_PROD, WS_PROD_THREADS);   // every product warp is done reading K
       if (active) store_acc_to_tile(acc, Ks, ldb, sA, sB, 0, lane);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // t is bulk-copied out by the support warps
-      bar_sync(WS_BAR_PROD, ROW_THREADS);
-      bar_arrive(WS_T_READY + b, WS_THREADS);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // t is bulk-copied out by the finish warps
+      bar_sync(WS_BAR_PROD, WS_PROD_THREADS);
+      bar_arrive(WS_T_READY + b, WS_N_PF);
       RT_TICK(3);
       // ---- u = H^T t ----
       zero_acc(acc);
@@ -881,34 +925,36 @@ __global__ void __launch_bounds__(WS_THREADS, 1) row_fwd_ws_kernel(const __grid_
         frag_segment<true>(acc[1], G, MP, Ks, ldb, sB, 0, lane, ring, frag_start(W, MP, sA, false, lane));
       }
       RT_TICK(4);
-      bar_sync(WS_T_DONE + b, WS_THREADS);  // all product warps are done reading t, and so are the support warps
+      bar_sync(WS_T_DONE + b, WS_N_PF);     // all product warps are done reading t, and so are the finish warps
       RT_TICK(5);
       if (active) store_acc_to_tile(acc, Ks, ldb, sA, sB, 0, lane);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      bar_sync(WS_BAR_PROD, ROW_THREADS);
-      bar_arrive(WS_U_READY + b, WS_THREADS);
+      bar_arrive(WS_U_READY + b, WS_N_PF);
       RT_TICK(6);
     }
     cp_async_wait_group<0>();     // the chained look-ahead of the last segment
     RT_FLUSH(0);
     return;
   }
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_SUPPORT_REGS));
+  if (n == 0) return;
 
-  // =========================== support warps ===========================
-  const unsigned uxrep = (unsigned)a.xrep, uprep = (unsigned)a.prep;
-  const unsigned ueps = a.eps_mod >= a.R ? 0u : (unsigned)a.eps_mod;       // 0: eps index == row
-  double (*s1s)[MAX_MP] = sm.s12;
-  double (*s2s)[MAX_MP] = sm.s12 + XMAX;
-  auto ssync = [&]() { bar_sync(WS_BAR_SUPP, ROW_THREADS); };
-  auto tile_of = [&](unsigned i) { return blockIdx.x + i * gridDim.x; };
-  // row data of the tile after the one being built, prefetched into registers: threads 0..31 a row's (mean, variance,
-  // normal) or its direct f, threads 32.. one coordinate of one of the tile's distinct x rows
-  double pf_a = 0.0, pf_b = 1.0, pf_c = 0.0;
-  auto prefetch = [&](unsigned i) {
-    if (i >= n) return;
-    const unsigned row0 = tile_of(i) * TR;
-    if (tid < TR) {
-      const unsigned row = row0 + tid;
+  if (role == 1) {
+    // =========================== build warps ===========================
+    //   stage 2, tile i:      K(Z, rows): warp <-> 2 rows, lane <-> inducing point of a 32-chunk:
+    //                         k = s1 (v f z_f + a_f E_f) + s2
+    //   stage 1, tile i + 1:  thread (j, half): a1 E1 and a2 E2 between inducing point j and two of the tile's (at most
+    //                         four) distinct x, read straight from global memory;  warp 15 also: the tile's rows -> f,
+    //                         v f, k_xx, which x (row data prefetched into registers one iteration earlier)
+    const unsigned uxrep = (unsigned)a.xrep, uprep = (unsigned)a.prep;
+    const unsigned ueps = a.eps_mod >= a.R ? 0u : (unsigned)a.eps_mod;       // 0: eps index == row
+    auto bsync = [&]() { bar_sync(WS_BAR_BUILD, WS_BUILD_THREADS); };
+    const bool rows_warp = warp == WS_BUILD_WARPS - 1;
+    // row data of the tile after the one being prepared: lane <-> row: (mean, variance, normal) or its direct f
+    double pf_a = 0.0, pf_b = 1.0, pf_c = 0.0;
+    auto prefetch = [&](unsigned i) {
+      if (i >= n || !rows_warp) return;
+      const unsigned row = tile_of(i) * TR + lane;
       pf_a = 0.0; pf_b = 1.0; pf_c = 0.0;
       if (row < R) {
         if (a.f_direct) {
@@ -920,93 +966,107 @@ __global__ void __launch_bounds__(WS_THREADS, 1) row_fwd_ws_kernel(const __grid_
           pf_c = a.eps[ueps ? row % ueps : row];
         }
       }
-    } else if (tid < TR + XMAX * a.d) {
-      const int c = (tid - TR) / a.d, cc = (tid - TR) - c * a.d;
-      const unsigned xi = row0 / uxrep + c;
-      const unsigned last = min(R - 1, row0 + TR - 1) / uxrep;
-      pf_a = xi <= last ? a.x[(size_t)xi * a.d + cc] : 0.0;
-    }
-  };
-  // K(Z_l, rows of tile i) into buffer i & 1 (its previous contents must have been released)
-  auto build = [&](unsigned i) {
-    const int b = i & 1;
-    double* Ks = tile_buf(b);
-    const unsigned row0 = tile_of(i) * TR;
-    const int nvalid = (int)min((unsigned)TR, R - row0);
-    const unsigned xi0 = row0 / uxrep;
-    if (tid < TR) {
-      double f = 0.0;
-      if (tid < nvalid) f = a.f_direct ? pf_a : pf_a + sqrt(fmax(pf_b, kMinVariance)) * pf_c;
-      sm.fs[tid] = f;
-      sm.kxx[b][tid] = sm.kf.a1 * (sm.kf.vlin * f * f + sm.kf.af) + sm.kf.a2;
-      sm.xsel[tid] = tid < nvalid ? (int)((row0 + tid) / uxrep - xi0) : 0;
-    } else if (tid < TR + XMAX * a.d) {
-      const int c = (tid - TR) / a.d;
-      sm.xs[c][(tid - TR) - c * a.d] = pf_a;
-    }
-    ssync();
-    prefetch(i + 1);
-    // (a) thread j: a1 E1 and a2 E2 between inducing point j and each distinct x of the tile
-    const int nx = (int)((row0 + nvalid - 1) / uxrep - xi0) + 1;
-    if (tid < MP) {
-      const KernFast& kf = sm.kf;
-      const bool jok = tid < a.M;
-      double D1[XMAX], D2[XMAX];
-#pragma unroll
-      for (int q = 0; q < XMAX; ++q) { D1[q] = kf.la1; D2[q] = kf.la2; }
-      for (int c = 0; c < a.d; ++c) {          // dimensions in ascending order, like every other build of K
-        const double z = jok ? __ldg(a.Zx + (size_t)tid * a.d + c) : 0.0;
-        const double2 cc = kf.cc[c];
-#pragma unroll
-        for (int q = 0; q < XMAX; ++q)
-          if (q < nx) {
-            const double df = sm.xs[q][c] - z;
-            const double d2 = df * df;
-            D1[q] = fma(d2, cc.x, D1[q]);
-            D2[q] = fma(d2, cc.y, D2[q]);
+    };
+    auto stage1 = [&](unsigned i) {
+      WsScratch& sc = sm.scr[i & 1];
+      const unsigned row0 = tile_of(i) * TR;
+      const int nvalid = (int)min((unsigned)TR, R - row0);
+      const unsigned xi0 = row0 / uxrep;
+      const int nx = (int)((row0 + nvalid - 1) / uxrep - xi0) + 1;
+      {
+        const int j = tid & (MAX_MP - 1), q0 = 2 * (tid / MAX_MP);       // this thread's inducing point and first x
+        if (j < MP && q0 < nx) {
+          const KernFast& kf = sm.kf;
+          const bool jok = j < a.M, two = q0 + 1 < nx;
+          const double* x0 = a.x + (size_t)(xi0 + q0) * a.d;
+          const double* x1 = two ? x0 + a.d : x0;
+          double D1[2] = {kf.la1, kf.la1}, D2[2] = {kf.la2, kf.la2};
+          for (int c = 0; c < a.d; ++c) {          // dimensions in ascending order, like every other build of K
+            const double2 cc = kf.cc[c];
+            const double z = sm.zsT[c][j];
+            const double da = __ldg(x0 + c) - z, db = __ldg(x1 + c) - z;
+            const double da2 = da * da, db2 = db * db;
+            D1[0] = fma(da2, cc.x, D1[0]); D2[0] = fma(da2, cc.y, D2[0]);
+            D1[1] = fma(db2, cc.x, D1[1]); D2[1] = fma(db2, cc.y, D2[1]);
           }
-      }
-#pragma unroll
-      for (int q = 0; q < XMAX; ++q)
-        if (q < nx) {
-          s1s[q][tid] = jok ? exp2_tab(D1[q], sm.e2tab) : 0.0;
-          s2s[q][tid] = jok ? exp2_tab(D2[q], sm.e2tab) : 0.0;
+          sc.s12[q0][j] = jok ? exp2_tab(D1[0], sm.e2tab) : 0.0;
+          sc.s12[XMAX + q0][j] = jok ? exp2_tab(D2[0], sm.e2tab) : 0.0;
+          if (two) {
+            sc.s12[q0 + 1][j] = jok ? exp2_tab(D1[1], sm.e2tab) : 0.0;
+            sc.s12[XMAX + q0 + 1][j] = jok ? exp2_tab(D2[1], sm.e2tab) : 0.0;
+          }
         }
-    }
-    ssync();
-    // (b) warp <-> RPW rows, lane <-> inducing point of a 32-chunk: k = s1 (v f z_f + a_f E_f) + s2
-    {
-      const KernFast& kf = sm.kf;
-      const int rbase = warp * RPW;
-      double f[RPW], vf[RPW];
-      int xs_[RPW];
+      }
+      if (rows_warp) {
+        double f = 0.0;
+        if (lane < nvalid) f = a.f_direct ? pf_a : pf_a + sqrt(fmax(pf_b, kMinVariance)) * pf_c;
+        sc.fs[lane] = f;
+        sc.vfs[lane] = sm.kf.vlin * f;
+        sm.kxx[i & 3][lane] = sm.kf.a1 * (sm.kf.vlin * f * f + sm.kf.af) + sm.kf.a2;
+        sc.xsel[lane] = lane < nvalid ? (int)((row0 + lane) / uxrep - xi0) : 0;
+        prefetch(i + 1);
+      }
+    };
+    auto stage2 = [&](unsigned i) {
+      const WsScratch& sc = sm.scr[i & 1];
+      double* Ks = tile_buf(i & 1);
+      const int nvalid = (int)min((unsigned)TR, R - tile_of(i) * TR);
+      const double laf = sm.kf.laf, cf = sm.kf.cf;
+      const int r0 = warp * WS_ROWS_PER_WARP;
+      double f[WS_ROWS_PER_WARP], vf[WS_ROWS_PER_WARP];
+      int so[WS_ROWS_PER_WARP];                      // offset of the row's x-kernel values in s12
 #pragma unroll
-      for (int r = 0; r < RPW; ++r) { f[r] = sm.fs[rbase + r]; vf[r] = kf.vlin * f[r]; xs_[r] = sm.xsel[rbase + r]; }
-      const double laf = kf.laf, cf = kf.cf;
+      for (int r = 0; r < WS_ROWS_PER_WARP; ++r) {
+        f[r] = sc.fs[r0 + r]; vf[r] = sc.vfs[r0 + r];
+        so[r] = sc.xsel[r0 + r] * MAX_MP + lane;
+      }
+      const double* s12 = &sc.s12[0][0];
       for (int ch = 0; ch < MP / 32; ++ch) {
         const int j = 32 * ch + lane;
         const double zf = sm.zfs[j];
+        double k[WS_ROWS_PER_WARP];
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) {
+        for (int r = 0; r < WS_ROWS_PER_WARP; ++r) {
           const double dff = f[r] - zf;
           const double Ef = exp2_tab(fma(dff * dff, cf, laf), sm.e2tab);
-          const double k = fma(s1s[xs_[r]][j], fma(vf[r], zf, Ef), s2s[xs_[r]][j]);
-          Ks[(size_t)(rbase + r) * ldb + j] = rbase + r < nvalid ? k : 0.0;
+          k[r] = fma(s12[so[r] + 32 * ch], fma(vf[r], zf, Ef), s12[so[r] + 32 * ch + XMAX * MAX_MP]);
         }
+#pragma unroll
+        for (int r = 0; r < WS_ROWS_PER_WARP; ++r) Ks[(size_t)(r0 + r) * ldb + j] = r0 + r < nvalid ? k[r] : 0.0;
       }
+    };
+    prefetch(0);
+    stage1(0);
+    bsync();
+    for (unsigned i = 0; i < n; ++i) {
+      const int b = i & 1;
+      RT_TICKW(1, 0);
+      if (i >= 2) bar_sync(WS_BUF_FREE + b, WS_N_FB);      // u of tile i - 2 has left the buffer
+      RT_TICKW(1, 1);
+      stage2(i);
+      RT_TICKW(1, 2);
+      bsync();      // K(i) complete, scratch of tile i free
+      bar_arrive(WS_K_READY + b, WS_N_K);
+      RT_TICKW(1, 3);
+      if (i + 1 < n) stage1(i + 1);      // off the path the product warps wait on: runs while u(i - 1) leaves its buffer
+      RT_TICKW(1, 4);
+      bsync();      // scratch of tile i + 1 complete
+      RT_TICKW(1, 5);
     }
-    ssync();      // also: fs / xsel / s12 are free for the next build
-    bar_arrive(WS_K_READY + b, WS_THREADS);
-  };
-  // row sums over the tile in shared memory: thread <-> (row = tid / 8, columns tid % 8 + 8 k); 8-lane fold
-  const int srow = tid >> 3, spart = tid & 7;
-  auto fold8 = [&](double v) {
+    RT_FLUSH(1);
+    return;
+  }
+
+  // =========================== finish warps ===========================
+  // row sums over the tile in shared memory: thread <-> (row = tid / 4, columns tid % 4 + 4 k): a half-warp's 16
+  // addresses fall into 16 different 8-byte banks (ldb % 16 == 4); 4-lane fold
+  const int srow = tid >> 2, spart = tid & 3;
+  auto fold4 = [&](double v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
     return v;
   };
-  // bulk (TMA engine) copies of the tile's valid rows to dst[R][MP], issued by the group's warp 0, which also waits
+  // bulk (TMA engine) copies of the tile's valid rows to dst[R][MP], issued by the role's warp 0, which also waits
   // until the engine has read them (the buffer is rewritten next)
   auto bulk_rows_out = [&](double* dst, const double* Ks, unsigned row0, int nvalid) {
     if (warp == 0) {
@@ -1019,59 +1079,56 @@ __global__ void __launch_bounds__(WS_THREADS, 1) row_fwd_ws_kernel(const __grid_
     }
   };
   auto bulk_wait_read = [&]() { if (warp == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); };
-  // t of tile i is in its buffer: |t|^2 and beta . t per row, bulk store of t; then u may replace it
-  auto finish_t = [&](unsigned i) {
-    const int b = i & 1;
-    const double* Ks = tile_buf(b);
-    const unsigned row0 = tile_of(i) * TR;
-    const int nvalid = (int)min((unsigned)TR, R - row0);
-    bar_sync(WS_T_READY + b, WS_THREADS);
-    if (a.Tsave) bulk_rows_out(a.Tsave, Ks, row0, nvalid);
-    double q = 0.0, m = 0.0;
-    const double* rowp = Ks + (size_t)srow * ldb + spart;
-    for (int k = 0; k < MP; k += 8) {
-      const double v = rowp[k];
-      q = fma(v, v, q);
-      m = fma(sm.beta[spart + k], v, m);
-    }
-    q = fold8(q); m = fold8(m);
-    if (spart == 0) { sm.q1[b][srow] = q; sm.mu[b][srow] = m; }
-    if (a.Tsave) bulk_wait_read();
-    bar_arrive(WS_T_DONE + b, WS_THREADS);
-  };
-  // u of tile i is in its buffer: |u|^2 per row, mean / variance of the tile's rows, bulk store of u; the buffer is free
-  auto finish_u = [&](unsigned i) {
-    const int b = i & 1;
-    const double* Ks = tile_buf(b);
-    const unsigned row0 = tile_of(i) * TR;
-    const int nvalid = (int)min((unsigned)TR, R - row0);
-    bar_sync(WS_U_READY + b, WS_THREADS);
-    if (a.Usave) bulk_rows_out(a.Usave, Ks, row0, nvalid);
-    double q = 0.0;
-    const double* rowp = Ks + (size_t)srow * ldb + spart;
-    for (int k = 0; k < MP; k += 8) { const double v = rowp[k]; q = fma(v, v, q); }
-    q = fold8(q);
-    if (spart == 0 && srow < nvalid) {
-      const double c = sm.kxx[b][srow] - sm.q1[b][srow];
-      const double v = (a.training ? fmax(c, 0.0) : c) + q;
-      a.mu[row0 + srow] = sm.mu[b][srow];
-      a.var[row0 + srow] = v;
-      if (a.craw) a.craw[row0 + srow] = c;
-      if (a.training && c < 0.0 && a.clamp_count) atomicAdd(a.clamp_count, 1u);
-    }
-    if (a.Usave) bulk_wait_read();
-    ssync();      // every support warp is done with the buffer (and the engine has read it)
-  };
-
-  if (n == 0) return;
-  prefetch(0);
-  build(0);
   for (unsigned i = 0; i < n; ++i) {
-    if (i >= 1) finish_u(i - 1);
-    if (i + 1 < n) build(i + 1);
-    finish_t(i);
+    const int b = i & 1;
+    const double* Ks = tile_buf(b);
+    const unsigned row0 = tile_of(i) * TR;
+    const int nvalid = (int)min((unsigned)TR, R - row0);
+    const double* rowp = Ks + (size_t)srow * ldb + spart;
+    // ---- t is in the buffer: |t|^2 and beta . t per row, bulk store of t; then u may replace it ----
+    RT_TICKW(2, 0);
+    bar_sync(WS_T_READY + b, WS_N_PF);
+    RT_TICKW(2, 1);
+    if (a.Tsave) bulk_rows_out(a.Tsave, Ks, row0, nvalid);
+    {
+      double q = 0.0, m = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < MP; k += 4) {
+        const double v = rowp[k];
+        q = fma(v, v, q);
+        m = fma(sm.beta[spart + k], v, m);
+      }
+      q = fold4(q); m = fold4(m);
+      if (spart == 0) { sm.q1[b][srow] = q; sm.mu[b][srow] = m; }
+    }
+    RT_TICKW(2, 2);
+    if (a.Tsave) bulk_wait_read();
+    bar_arrive(WS_T_DONE + b, WS_N_PF);
+    RT_TICKW(2, 3);
+    // ---- u is in the buffer: |u|^2 per row, mean / variance of the tile's rows, bulk store of u; buffer released ----
+    bar_sync(WS_U_READY + b, WS_N_PF);
+    RT_TICKW(2, 4);
+    if (a.Usave) bulk_rows_out(a.Usave, Ks, row0, nvalid);
+    {
+      double q = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < MP; k += 4) { const double v = rowp[k]; q = fma(v, v, q); }
+      q = fold4(q);
+      if (spart == 0 && srow < nvalid) {
+        const double c = sm.kxx[i & 3][srow] - sm.q1[b][srow];
+        const double v = (a.training ? fmax(c, 0.0) : c) + q;
+        a.mu[row0 + srow] = sm.mu[b][srow];
+        a.var[row0 + srow] = v;
+        if (a.craw) a.craw[row0 + srow] = c;
+        if (a.training && c < 0.0 && a.clamp_count) atomicAdd(a.clamp_count, 1u);
+      }
+    }
+    RT_TICKW(2, 5);
+    if (a.Usave) bulk_wait_read();
+    if (i + 2 < n) bar_arrive(WS_BUF_FREE + b, WS_N_FB);
+    RT_TICKW(2, 6);
   }
-  finish_u(n - 1);
+  RT_FLUSH(2);
 }
 
 // Backward through the covariance function for one tile: Ks holds dk = d loss / d K(z_j, row r).  Same thread mapping
@@ -1567,6 +1624,12 @@ __global__ void reduce_partials_kernel(const double* __restrict__ part, int nblo
 constexpr int SY_KB = 32, SY_WARPS = 12, SY_THREADS = SY_WARPS * 32, SY_STAGES = 3;
 
 __host__ __device__ inline size_t syrk_stage_doubles(int MP) { return (size_t)SY_KB * (MP + 4) + 3 * SY_KB; }
+// b = sum_r dmu_r t_r rides along: every group of CTAs takes an equal share of the MP columns, a thread one column and
+// one of SY_ALPHA_PARTS slices of a stage's rows.  (First version: the first MP threads of group 0 only, 32 FMAs per
+// stage each.  Next to warps that stream DMMAs an FP64 instruction of another warp waits ~80 cycles for its turn, so
+// those 8 warps fell 2.5k cycles per 6k-cycle stage behind and their CTAs - a third of the grid - set the kernel time.)
+constexpr int SY_ALPHA_PARTS = 4;
+__host__ __device__ inline size_t syrk_alpha_doubles(int MP, int nchunk) { return (size_t)nchunk * SY_ALPHA_PARTS * MP; }
 __host__ __device__ inline int syrk_nblocks(int MP) { const int nb = MP / 32; return nb * (nb + 1) / 2; }
 
 __global__ void __launch_bounds__(SY_THREADS, 1)
@@ -1596,7 +1659,12 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
   const long long rbeg = (long long)chunk * rows_per;
   const long long rend = min(R, rbeg + rows_per);
   const int nst = rend > rbeg ? (int)((rend - rbeg + SY_KB - 1) / SY_KB) : 0;
-  const bool do_alpha = which == 0 && group == 0 && part_alpha != nullptr && dmu != nullptr;
+  const bool do_alpha = which == 0 && part_alpha != nullptr && dmu != nullptr;
+  const int acols = (MP + (int)gridDim.x - 1) / (int)gridDim.x;                 // columns of b per group
+  const int aparts = acols * 4 <= SY_THREADS ? 4 : (acols * 2 <= SY_THREADS ? 2 : 1);
+  const int apart = tid / acols, acol = group * acols + tid % acols;
+  const bool alpha_thread = do_alpha && apart < aparts && acol < MP && acol < (group + 1) * acols;
+  const int ak0 = apart * (SY_KB / aparts), ak1 = ak0 + SY_KB / aparts;
   const unsigned row_bytes = (unsigned)MP * sizeof(double);
   // the three per-row arrays travel as 256-byte bulk copies when they are 16-byte aligned (always, for fresh
   // allocations); otherwise, and for the ragged last stage, warp 0 loads them itself
@@ -1678,11 +1746,10 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
           for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
       }
     }
-    if (do_alpha && tid < MP) {
+    if (alpha_thread) {
+      for (int k = ak0; k < ak1; k += 4)
 #pragma unroll
-      for (int k = 0; k < SY_KB; k += 4)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) al[c] = fma(ws[SY_KB + k + c], Ts[(size_t)(k + c) * ld + tid], al[c]);
+        for (int c = 0; c < 4; ++c) al[c] = fma(ws[SY_KB + k + c], Ts[(size_t)(k + c) * ld + acol], al[c]);
     }
     __syncthreads();   // everyone is done with this slot: refill it with the stage SY_STAGES ahead
     if (warp == 0 && it + SY_STAGES < nst) issue(it + SY_STAGES);
@@ -1696,7 +1763,13 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
 #pragma unroll
         for (int e = 0; e < 2; ++e) out[(8 * x + g) * 32 + 8 * y + 2 * t + e] = acc[x][y][e];
   }
-  if (do_alpha && tid < MP) part_alpha[(size_t)chunk * MP + tid] = (al[0] + al[1]) + (al[2] + al[3]);
+  if (do_alpha) {       // slices a thread count does not reach stay zero
+    if (alpha_thread) part_alpha[((size_t)chunk * SY_ALPHA_PARTS + apart) * MP + acol] = (al[0] + al[1]) + (al[2] + al[3]);
+    for (int idx = tid; idx < (SY_ALPHA_PARTS - aparts) * acols; idx += SY_THREADS) {
+      const int pz = aparts + idx / acols, cz = group * acols + idx % acols;
+      if (cz < MP) part_alpha[((size_t)chunk * SY_ALPHA_PARTS + pz) * MP + cz] = 0.0;
+    }
+  }
 }
 
 __global__ void syrk_reduce_kernel(const double* __restrict__ part, int nchunk, int MP, double* __restrict__ A,
@@ -1848,7 +1921,7 @@ int syrk_nchunk(int MP, long long R) {
 
 size_t syrk_part_doubles(int MP, long long R) { return (size_t)syrk_nblocks(MP) * syrk_nchunk(MP, R) * 1024; }
 
-// part: syrk_part_doubles(MP, R) doubles of scratch; part_alpha: nchunk * MP doubles (which == 0 only)
+// part: syrk_part_doubles(MP, R) doubles of scratch; part_alpha: syrk_alpha_doubles(MP, nchunk) doubles (which == 0 only)
 // the SYRK proper (DMMA-bound): per-chunk partial blocks into `part`, partial b into part_alpha (which == 0)
 int launch_syrk_main(const double* K, const double* dvar, const double* craw, int which, int MP, long long R,
                      double* part, const unsigned int* clamp_count, const double* dmu, double* part_alpha,
@@ -1888,7 +1961,7 @@ int launch_syrk_reduce(int which, int MP, long long R, const double* part, doubl
   const int nc = syrk_nchunk(MP, R);
   MOBO_LAUNCH("syrk_reduce_kernel", st, syrk_reduce_kernel<<<(MP * MP + 255) / 256, 256, 0, st>>>(part, nc, MP, A, which, clamp_count, clamp_flag_out));
   if (which == 0 && part_alpha && dalpha)
-    MOBO_LAUNCH("reduce_partials_kernel", st, reduce_partials_kernel<<<(MP + 3) / 4, 128, 0, st>>>(part_alpha, nc, MP, MP, dalpha, 0));
+    MOBO_LAUNCH("reduce_partials_kernel", st, reduce_partials_kernel<<<(MP + 3) / 4, 128, 0, st>>>(part_alpha, nc * SY_ALPHA_PARTS, MP, MP, dalpha, 0));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

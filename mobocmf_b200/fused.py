@@ -32,7 +32,7 @@ class StepDesc(ctypes.Structure):
     _fields_ = [("L", ctypes.c_int), ("d", ctypes.c_int), ("M", ctypes.c_int), ("S", ctypes.c_int),
                 ("B", ctypes.c_longlong), ("num_data", ctypes.c_longlong), ("jitter", ctypes.c_double),
                 ("x", _dp), ("y", _dp), ("fid", _dp), ("layer", LayerDesc * MAX_LAYERS), ("out", _dp),
-                ("workspace", _dp), ("accumulate", ctypes.c_int)]
+                ("workspace", _dp), ("accumulate", ctypes.c_int), ("ctx", _dp)]
 
 
 class AdamTensor(ctypes.Structure):
@@ -88,6 +88,21 @@ class FusedELBOStep(object):
         self._ws_pinned = set()
         self._desc = StepDesc()
         self._sig = None
+        # this step's own side stream + events (include/mobocmf_b200.h: mobo_step_ctx_create): concurrently trained
+        # models must not share one, their operator-chain backwards would serialise on it
+        with torch.cuda.device(self.device):
+            self._ctx = self.lib.mobo_step_ctx_create()
+        if not self._ctx:
+            raise RuntimeError("mobocmf_b200: mobo_step_ctx_create failed")
+
+    def __del__(self):
+        ctx, self._ctx = getattr(self, "_ctx", None), None
+        if ctx:
+            try:
+                torch.cuda.synchronize(self.device)     # no step that uses the context may still be in flight
+                self.lib.mobo_step_ctx_destroy(ctx)
+            except Exception:
+                pass
 
     @staticmethod
     def supported(model):
@@ -128,6 +143,7 @@ class FusedELBOStep(object):
         D.L, D.d, D.M = self.L, self.d, self.M
         D.out = self.out.data_ptr()
         D.accumulate = 0
+        D.ctx = self._ctx
         D.jitter = float(self.layers[0].variational_strategy.jitter_val)
         self._keep = []
         for l, (layer, lik) in enumerate(zip(self.layers, self.liks)):

@@ -12,7 +12,7 @@ def header_functions():
     src = open(os.path.join(ROOT, "include", "mobocmf_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(?:int|size_t|void|long long)\s+(mobo_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(?:int|size_t|void\s*\*|void|long long)\s*(mobo_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = m.group(2).strip()
         out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
     return out
@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert len(decl) >= 12
     for name in decl:
         assert hasattr(lib, name), name
-    assert lib.mobo_abi_version() == 101
+    assert lib.mobo_abi_version() == 102
 
 
 def test_ctypes_signatures_match_header():

@@ -92,6 +92,23 @@ int main(int argc, char** argv) {
       else printf("  %-28s %8.1f us / iteration (%d launches)\n", a.name, us, a.c / iters);
     }
   }
+  {   // SYRK alone, with and without the b = sum dmu t accumulation of group 0
+    double* part; cudaMalloc(&part, (mobo::syrk_part_doubles(MP, R) + mobo::syrk_alpha_doubles(MP, mobo::syrk_nchunk(MP, R))) * 8);
+    double* pal = part + mobo::syrk_part_doubles(MP, R);
+    for (int variant = 0; variant < 2; ++variant) {
+      float tt = 0;
+      for (int it = 0; it < reps + 2; ++it) {
+        cudaEventRecord(e[0]);
+        mobo::launch_syrk_main(Ts, dvar, craw, 0, MP, R, part, clamp, variant ? nullptr : dmu, pal, nullptr);
+        cudaEventRecord(e[1]); cudaEventSynchronize(e[1]);
+        float x; cudaEventElapsedTime(&x, e[0], e[1]);
+        if (it >= 2) tt += x;
+      }
+      tt /= reps;
+      printf("syrk_kernel alone %-18s %8.1f us  %6.2f TF  %.3f of peak\n", variant ? "(no b accumulation)" : "(with b)", tt * 1e3,
+             (double)M * M * R / tt / 1e9, (double)M * M * R / tt / 1e9 / peak);
+    }
+  }
 #ifdef ROW_TIMING
   {
     mobo_layer_rows_fwd(1, d, M, Zx, zf, theta, ops, x, S, mu_prev, var_prev, S, eps, R, nullptr, R, 1, mu, var, craw, clamp,
@@ -111,6 +128,16 @@ int main(int argc, char** argv) {
     for (int b = 0; b < grid; ++b) for (int k = 0; k < 12; ++k) { s[k] += (double)t[0][b][k]; tot += (double)t[0][b][k]; }
     printf("forward kernel (training launch: saves t / u), cycles of thread 0 summed over %d CTAs: share per phase\n", grid);
     for (int k = 0; k < 12; ++k) printf("  %-30s %6.2f %%   %9.0f cycles per CTA\n", names[k], 100.0 * s[k] / tot, s[k] / grid);
+    if (pp) {
+      const char* bnames[10] = {"(loop top)", "WAIT: buffer free", "stage 2: K of tile i", "sync, signal K ready", "stage 1: x-kernels of tile i+1", "sync", "-", "-", "-", "-"};
+      const char* fnames[10] = {"(loop top)", "WAIT: t ready", "t sums", "bulk wait t, signal", "WAIT: u ready", "u sums, epilogue", "bulk wait u, signal", "-", "-", "-"};
+      for (int w = 1; w <= 2; ++w) {
+        double tt = 0, ss[10] = {0};
+        for (int b = 0; b < grid; ++b) for (int k = 0; k < 10; ++k) { ss[k] += (double)t[w][b][k]; tt += (double)t[w][b][k]; }
+        printf("%s warps (thread 0 of the role):\n", w == 1 ? "build" : "finish");
+        for (int k = 0; k < 10; ++k) printf("  %-30s %6.2f %%   %9.0f cycles per CTA\n", w == 1 ? bnames[k] : fnames[k], 100.0 * ss[k] / tt, ss[k] / grid);
+      }
+    }
   }
 #endif
   return 0;
