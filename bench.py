@@ -147,11 +147,17 @@ def run_ours(args):
         broadcast_parameters(model)
         fstep = FusedELBOStep(model, elbo)
         opt = Adam([{"params": params}], lr=0.001)
+        comm = torch.cuda.Stream(device=dev) if world > 1 and args.allreduce == "overlapped" else None
 
         def one_step(xb, yb, fb):
             loss, _ = fstep(xb, yb, fb, num_samples=S)
             if world > 1:
-                fstep.flat.all_reduce()          # ONE all-reduce of the flat gradient buffer (NCCL over NVLink)
+                if comm is not None:
+                    # the three M x M blocks d L_q (1.5 of the 1.6 MB) leave as soon as their layer's operator-chain
+                    # backward is done, behind the lower layers' row kernels; only the ~6 KB tail waits for the step
+                    fstep.flat.all_reduce_overlapped(fstep.wait_bucket, comm)
+                else:
+                    fstep.flat.all_reduce()      # ONE all-reduce of the flat gradient buffer (NCCL over NVLink)
             opt.step()
             return loss
     else:
@@ -426,7 +432,10 @@ def bench_small_configs(dev, steps=200):
             e1.record()
             torch.cuda.synchronize()
             res[mode + "_us_per_step"] = round(e0.elapsed_time(e1) / steps * 1e3, 1)
+            if mode == "eager":
+                res["kernels_per_step"] = _lib_launches_per_step(fn)
         res["steps_per_s"] = round(1e6 / res["graph_us_per_step"], 1)
+        res["launch_floor"] = launch_floor(dev, res["kernels_per_step"])
         # K = 6 independent black-box models (4 objectives + 2 constraints, BASELINE.json configs[4]) trained round-robin,
         # one CUDA stream and one graph each (BlackBoxMFDGPFitter(concurrent_models=True)): their latency-bound chains
         # overlap on the GPU.  Wall clock between two device synchronisations.
@@ -456,6 +465,47 @@ def bench_small_configs(dev, steps=200):
             res["conditioned_iteration_ms"] = bench_conditioned(dev, x, y, fid)
         res["get_nextpoint_coupled"] = bench_optimize(dev, x, y, fid)
         out[name] = res
+    return out
+
+
+def _lib_launches_per_step(fn):
+    from mobocmf_b200 import _lib
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    fn()
+    torch.cuda.synchronize()
+    return int(_lib.launch_count() - n0)
+
+
+def launch_floor(dev, nodes, reps=200):
+    """what a step of `nodes` kernels costs when the kernels do nothing - a CUDA graph of `nodes`
+    one-element kernels in ONE dependent chain (the upper bound of the step's critical path: its side-stream branches
+    shorten it) and the same number in two parallel chains."""
+    t = torch.zeros(2, device=dev)
+    out = {"nodes": nodes}
+    for name, chains in (("one_chain_us", 1), ("two_chains_us", 2)):
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        with torch.cuda.graph(g):
+            if chains == 2:
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(nodes // 2):
+                        t[1:2].add_(0.0)
+            for _ in range(nodes - (nodes // 2 if chains == 2 else 0)):
+                t[0:1].add_(0.0)
+            if chains == 2:
+                torch.cuda.current_stream().wait_stream(side)
+        for _ in range(5):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = round(e0.elapsed_time(e1) / reps * 1e3, 1)
     return out
 
 
@@ -911,6 +961,8 @@ def main():
                     help="fused: mobo_elbo_step + mobo_adam (product hot loop); composable: autograd over the same kernels")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: one 1024 x 64 step unit per GPU; strong: one 1024 x 64 step split over the GPUs")
+    ap.add_argument("--allreduce", default="overlapped", choices=["overlapped", "single"],
+                    help="multi-GPU gradient exchange: per-layer buckets behind the row kernels, or one all-reduce")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-acq", action="store_true", help="skip the acquisition sweep and the small-config legs")
     ap.add_argument("--no-parity", action="store_true", help="skip the CUDA-vs-oracle parity block")

@@ -163,6 +163,12 @@ size_t mobo_elbo_step_workspace_doubles(int L, int d, int M, int S, long long B)
  * the last step that used it has completed.  Returns NULL on a CUDA error. */
 void* mobo_step_ctx_create(void);
 void mobo_step_ctx_destroy(void* ctx);
+/* Makes `stream` wait until layer `layer`'s operator-chain backward of the LAST mobo_elbo_step enqueued with this
+ * context (accumulate == 0) has completed, i.e. until g_Lq of that layer is final - long before the step ends (the
+ * layers are processed high -> low).  For multi-GPU callers: the all-reduce of the large M x M gradient blocks can
+ * run behind the remaining row kernels; only the small gradients (m, hyper-parameters, noise) must wait for the end
+ * of the step.  Returns -2 for a NULL context / bad layer. */
+int mobo_step_ctx_wait_layer(void* ctx, int layer, void* stream);
 /* 0 serialises everything on the caller's stream (used by bench.py's per-kernel timing leg); default 1. */
 void mobo_step_side_stream(int on);
 int mobo_elbo_step(const mobo_step_desc* desc, void* stream);

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "mobo_step_side_stream": (None, [_c_i]),
     "mobo_step_ctx_create": (_c_dp, []),
     "mobo_step_ctx_destroy": (None, [_c_dp]),
+    "mobo_step_ctx_wait_layer": (_c_i, [_c_dp, _c_i, _c_dp]),
     "mobo_adam": (_c_i, [_c_i, _c_dp, _c_d, _c_d, _c_d, _c_d, _c_ll, _c_dp, _c_dp, _c_dp]),
     "mobo_adam_tick": (_c_i, [_c_dp, _c_dp, _c_dp]),
     "mobo_acq_moments": (_c_i, [_c_i, _c_i, _c_i, _c_i, _c_ll, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_d, _c_d,

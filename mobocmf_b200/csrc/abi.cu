@@ -394,12 +394,16 @@ StepLayout step_layout(int L, int d, int M, int S, long long B) {
 // not serialise on each other's side stream); a step without a context uses one per-device default, created under a
 // lock on first use - the only state this library keeps.
 namespace {
-struct SideCtx { int device = -1; cudaStream_t s = nullptr; cudaEvent_t fork[ST_MAX_LAYERS]; cudaEvent_t join = nullptr; };
+struct SideCtx {
+  int device = -1; cudaStream_t s = nullptr; cudaEvent_t fork[ST_MAX_LAYERS]; cudaEvent_t join = nullptr;
+  cudaEvent_t done[ST_MAX_LAYERS];      // layer l's operator-chain backward (its d L_q, d m, d theta shares) is complete
+};
 bool side_ctx_init(SideCtx& c) {
   if (cudaGetDevice(&c.device) != cudaSuccess) return false;
   if (cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking) != cudaSuccess) return false;
   for (int i = 0; i < ST_MAX_LAYERS; ++i)
-    if (cudaEventCreateWithFlags(&c.fork[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&c.fork[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.done[i], cudaEventDisableTiming) != cudaSuccess) return false;
   return cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) == cudaSuccess;
 }
 SideCtx* default_side_ctx() {
@@ -419,11 +423,16 @@ void* mobo_step_ctx_create(void) {
   if (!side_ctx_init(*c)) { delete c; return nullptr; }
   return c;
 }
+int mobo_step_ctx_wait_layer(void* ctx, int layer, void* stream) {
+  SideCtx* c = static_cast<SideCtx*>(ctx);
+  if (!c || layer < 0 || layer >= ST_MAX_LAYERS) return -2;
+  return cudaStreamWaitEvent((cudaStream_t)stream, c->done[layer], 0) == cudaSuccess ? 0 : -1;
+}
 void mobo_step_ctx_destroy(void* ctx) {
   SideCtx* c = static_cast<SideCtx*>(ctx);
   if (!c) return;
   if (c->s) cudaStreamDestroy(c->s);
-  for (int i = 0; i < ST_MAX_LAYERS; ++i) if (c->fork[i]) cudaEventDestroy(c->fork[i]);
+  for (int i = 0; i < ST_MAX_LAYERS; ++i) { if (c->fork[i]) cudaEventDestroy(c->fork[i]); if (c->done[i]) cudaEventDestroy(c->done[i]); }
   if (c->join) cudaEventDestroy(c->join);
   delete c;
 }
@@ -524,6 +533,9 @@ int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
                                 gl + ops_scal(MP) + SC_CLAMP, ss));
     MOBO_TRY(mobo_model_precompute_bwd(1, kinds + l, d, M, Zx + l, zf + l, theta + l, m + l, Lq + l, cops + l, gops + l,
                                        pre_work + l, dtheta_pre + l, dzf_pre + l, dm_pre + l, dLq + l, (void*)ss));
+    // d L_q of this layer is final (it is written straight into the caller's gradient): a multi-GPU caller may start
+    // its all-reduce now, behind the lower layers' row kernels (mobo_step_ctx_wait_layer)
+    if (scp && !D->accumulate && cudaEventRecord(sc.done[l], ss) != cudaSuccess) return -1;
     // main stream: dk = W^T dt and the covariance gradient
     RowArgs a;
     fill_row_args(a, kinds[l], d, M, Zx[l], zf[l], theta[l], ops[l], D->x, l == 0 ? 1 : S,

@@ -95,6 +95,12 @@ class FusedELBOStep(object):
         if not self._ctx:
             raise RuntimeError("mobocmf_b200: mobo_step_ctx_create failed")
 
+    def wait_bucket(self, k, stream):
+        """Makes ``stream`` wait until leading gradient block k of ``self.flat`` (d L_q of a layer) is final in the step
+        enqueued last (include/mobocmf_b200.h: mobo_step_ctx_wait_layer)."""
+        _lib.check(self.lib.mobo_step_ctx_wait_layer(self._ctx, self._bucket_layer[k],
+                                                     ctypes.c_void_p(stream.cuda_stream)), "mobo_step_ctx_wait_layer")
+
     def __del__(self):
         ctx, self._ctx = getattr(self, "_ctx", None), None
         if ctx:
@@ -133,8 +139,15 @@ class FusedELBOStep(object):
             if not p.requires_grad and p.grad is not None:
                 p.grad = None      # frozen since an earlier phase: torch's zero_grad would have dropped it too
         params = [p for p in self.model.parameters() if p.requires_grad]
-        if self.flat is None or [id(p) for p in self.flat.params] != [id(p) for p in params]:
-            self.flat = FlatGrads(params)
+        # the M x M blocks d L_q lead the flat buffer, highest layer first: the order in which the step completes them
+        # (FlatGrads.all_reduce_overlapped sends each behind the lower layers' row kernels)
+        first = [lay.variational_strategy._variational_distribution.chol_variational_covar for lay in self.layers[::-1]]
+        first = [p for p in first if p.requires_grad]
+        want = [id(p) for p in first] + [id(p) for p in params if not any(p is q for q in first)]
+        if self.flat is None or [id(p) for p in self.flat.params] != want:
+            self.flat = FlatGrads(params, first=first)
+            self._bucket_layer = [self.layers.index(lay) for lay in self.layers[::-1]
+                                  if lay.variational_strategy._variational_distribution.chol_variational_covar.requires_grad]
         elif not self.flat.attached():
             self.flat.reattach()
 

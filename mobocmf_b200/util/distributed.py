@@ -34,8 +34,13 @@ class FlatGrads(object):
     """One contiguous gradient buffer whose slices are the ``.grad`` of the given parameters, so that the kernels
     write every gradient straight into it and the cross-rank exchange is ONE all-reduce without packing copies."""
 
-    def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
+    def __init__(self, params, first=()):
+        """``first``: parameters whose gradients are laid out at the front of the buffer, in this order (the large
+        M x M blocks that ``all_reduce_overlapped`` sends early); the rest follow in the order of ``params``."""
+        ps = [p for p in params if p.requires_grad]
+        head = [p for p in first if p.requires_grad and any(p is q for q in ps)]
+        self.params = head + [p for p in ps if not any(p is q for q in head)]
+        self.n_first = len(head)
         if not self.params:
             raise ValueError("no trainable parameters")
         p0 = self.params[0]
@@ -65,6 +70,40 @@ class FlatGrads(object):
         """Sum the gradients over the ranks (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        return self.flat
+
+    def buckets(self):
+        """[(view of the flat buffer)] : one per leading block (``first``), then ONE for everything else."""
+        out = []
+        for p, o in zip(self.params[:self.n_first], self.offsets[:self.n_first]):
+            out.append(self.flat[o:o + p.numel()])
+        tail = self.offsets[self.n_first] if self.n_first < len(self.params) else self.flat.numel()
+        out.append(self.flat[tail:])
+        return out
+
+    def all_reduce_overlapped(self, ready=None, comm_stream=None, group=None):
+        """The same sum as ``all_reduce`` in ``n_first + 1`` pieces: leading block k is sent as soon as ``ready(k,
+        stream)`` has made the communication stream wait for it (FusedELBOStep.wait_bucket: the event the fused step
+        records when that layer's d L_q is final), i.e. behind the rest of the step; only the small tail waits for the
+        end of the step.  ``ready`` / ``comm_stream`` None (CPU, gloo): the pieces are sent in order on the spot."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return self.flat
+        bs = self.buckets()
+        if comm_stream is None:
+            for b in bs:
+                if b.numel():
+                    dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
+            return self.flat
+        main = torch.cuda.current_stream(self.flat.device)
+        works = []
+        for k, b in enumerate(bs[:-1]):
+            ready(k, comm_stream)
+            with torch.cuda.stream(comm_stream):
+                works.append(dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group, async_op=True))
+        if bs[-1].numel():
+            dist.all_reduce(bs[-1], op=dist.ReduceOp.SUM, group=group)     # on the main stream: after the step
+        for w in works:
+            w.wait()                                                        # main stream waits for the early pieces
         return self.flat
 
 

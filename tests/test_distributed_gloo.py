@@ -69,7 +69,21 @@ def _worker(rank, world_size, port, out_dir):
         grads = torch.autograd.grad(loss, list(h.ps))
         for p, g_ in zip(h.ps, grads):
             p.grad.copy_(g_)               # what the kernels do: write into the flat buffer's slices
+        before = flat.flat.clone()
         flat.all_reduce()
+        # the bucketed exchange (large blocks first, one tail) is the same sum: the chol blocks lead a second buffer
+        big = [p for k, p in zip(keys, h.ps) if "chol_variational_covar" in k][::-1]
+        flat2 = D.FlatGrads(list(h.ps), first=big)
+        assert flat2.n_first == len(big) == L and flat2.params[0] is big[0] and flat2.attached()
+        for p, g_ in zip(h.ps, grads):
+            p.grad.copy_(g_)
+        assert sum(b.numel() for b in flat2.buckets()) == flat2.flat.numel() == before.numel()
+        flat2.all_reduce_overlapped()
+        bucketed = {id(p): p.grad.clone() for p in h.ps}
+        flat.reattach()
+        for p in h.ps:                       # same per-parameter sums as the single all-reduce of the first layout
+            o = flat.offsets[[id(q) for q in flat.params].index(id(p))]
+            assert torch.equal(bucketed[id(p)].reshape(-1), flat.flat[o:o + p.numel()])
         vals = torch.arange(lo, hi, dtype=torch.float64) * (1.0 if rank == 0 else -1.0)
         full = D.gather_candidate_values(vals, x.shape[0])
         best = D.argmax_over_ranks(vals, lo)
@@ -125,3 +139,9 @@ def test_flat_grads_alias_and_reattach():
     flat.reattach()
     assert flat.attached()
     assert D.world() == (0, 1)
+    # leading blocks: the named parameters first, in the given order; buckets = one per leading block + one tail
+    f2 = D.FlatGrads(ps + [frozen], first=[ps[1], frozen])
+    assert f2.n_first == 1 and f2.params[0] is ps[1] and f2.offsets == [0, 5]
+    b = f2.buckets()
+    assert [x.numel() for x in b] == [5, 6] and b[0].data_ptr() == ps[1].grad.data_ptr()
+    assert f2.all_reduce_overlapped() is f2.flat          # no process group: a no-op
