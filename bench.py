@@ -327,8 +327,11 @@ def run_ours(args):
             M, d, L = cfg["M"], cfg["d"], cfg["L"]
             rows = [B] + [B * S] * (L - 1)       # this rank's rows (strong scaling: its shard)
             dl = [d] + [d + 1] * (L - 1)
+            fwd_l = [r * (2 * M * M + 2 * M + 3 * k * M) for r, k in zip(rows, dl)]
+            ws = "row_fwd_ws_kernel" in tot      # the S-sample rows of the upper layers run in the warp-specialised kernel
             alg_per_step = {
-                "row_fwd_kernel": sum(r * (2 * M * M + 2 * M + 3 * k * M) for r, k in zip(rows, dl)),
+                "row_fwd_kernel": fwd_l[0] if ws else sum(fwd_l),
+                "row_fwd_ws_kernel": sum(fwd_l[1:]),
                 "row_bwd_gemm_kernel": sum(r * (2 * M * M + 2 * M) for r in rows),
                 "syrk_kernel": sum(r * M * M for r in rows),
             }
@@ -347,6 +350,8 @@ def run_ours(args):
                                "launches_per_step": len(prof[top]) // nst, "ms_per_step": ms_top,
                                "algorithmic_gflop_per_step": alg_per_step[top] / 1e9,
                                "share_of_step": ms_top / ms_step}
+            out["roofline_by_kernel"] = {k: round(alg_per_step[k] / (tot[k] / nst * 1e-3) / 1e12 / FP64_PEAK_TFLOPS, 4)
+                                         for k in alg_per_step if k in tot and tot[k] > 0}
             out["kernel_ms_per_step"] = {k: round(v / nst, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}
             out["kernel_ms_note"] = ("CUDA-event time per kernel over %d extra steps run with the step's side stream "
                                      "serialised (mobo_step_side_stream(0)); in the timed region the operator-chain "
@@ -961,7 +966,7 @@ def main():
                     help="fused: mobo_elbo_step + mobo_adam (product hot loop); composable: autograd over the same kernels")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: one 1024 x 64 step unit per GPU; strong: one 1024 x 64 step split over the GPUs")
-    ap.add_argument("--allreduce", default="overlapped", choices=["overlapped", "single"],
+    ap.add_argument("--allreduce", default="single", choices=["overlapped", "single"],
                     help="multi-GPU gradient exchange: per-layer buckets behind the row kernels, or one all-reduce")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-acq", action="store_true", help="skip the acquisition sweep and the small-config legs")

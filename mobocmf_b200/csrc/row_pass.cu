@@ -1389,6 +1389,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "DONE_%=:\n"
       "}\n" ::"r"(addr), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 // bulk (TMA engine) global -> shared copy of `bytes` (multiple of 16, both sides 16-byte aligned), completion on `bar`
 __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -1456,6 +1459,14 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_gemm_kernel(const __gr
     if (warp == 0) stage_tile(tile);
     if (tid < TR) prefetch_rows(tile);
   }
+  // A-fragment stream as in the forward kernel (frag_segment): four segments per tile (H slab A, H slab B, W^T slab A,
+  // W^T slab B), each priming the ring for the next, so that no segment starts with an L2 round trip (4 per tile in the
+  // first version, ~6 % of a tile), and the half-zero diagonal blocks skip their zero DMMAs
+  if (active) {
+    const double2* first = frag_start(H, MP, sA, false, lane);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { cp_async16_cg(ring + lane + j * 32, first + j * 32); cp_async_commit_group(); }
+  }
   unsigned parity = 0;
   for (; tile < ntiles; tile += gridDim.x) {
     const long long row0 = tile * TR;
@@ -1468,7 +1479,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_gemm_kernel(const __gr
     if (active) {
       // ---- y = H u ----
       zero_acc(acc);
-      slab_gemm<false, BWD_NST, true>(acc, H, MP, BU, ldb, sA, sB, half, lane, ring);
+      frag_segment<false>(acc[0], H, MP, BU, ldb, sA, half, lane, ring, frag_start(H, MP, sB, false, lane));
+      frag_segment<false>(acc[1], H, MP, BU, ldb, sB, half, lane, ring, frag_start(WT, MP, sA, true, lane));
       // ---- dt = dmu beta - 2 dvar (mask t - y) ----
 #pragma unroll
       for (int sl = 0; sl < 2; ++sl)
@@ -1496,10 +1508,12 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_gemm_kernel(const __gr
     // ---- dk = W^T dt, straight from the accumulators to HBM ----
     if (active) {
       zero_acc(acc);
-      slab_gemm<true, BWD_NST, true>(acc, WT, MP, X, ldb, sA, sB, half, lane, ring);
+      frag_segment<true>(acc[0], WT, MP, X, ldb, sA, half, lane, ring, frag_start(WT, MP, sB, true, lane));
+      frag_segment<true>(acc[1], WT, MP, X, ldb, sB, half, lane, ring, frag_start(H, MP, sA, false, lane));
       store_acc_rows(acc, a.dk, row0, nvalid, MP, sA, sB, half, lane);
     }
   }
+  cp_async_wait_group<0>();     // the chained look-ahead of the last segment
 }
 
 // ---- through the covariance function: 4 warps x RPW rows per tile, 3 CTAs per SM ----
@@ -1616,12 +1630,15 @@ __global__ void reduce_partials_kernel(const double* __restrict__ part, int nblo
 // The lower triangle is cut into 32 x 32 blocks (36 at MP = 256), one block per warp, 12 warps per CTA, so every
 // DMMA is useful work and every warp carries the same load.  A CTA streams ALL MP columns of its chunk of rows
 // through a 3-stage bulk-copy (TMA engine) + mbarrier pipeline (32 rows per stage, one 2 KB copy per row) and each
-// warp reads its two column panels from there.
+// warp reads its two column panels from there.  A thirteenth warp is the producer: it refills a slot as soon as the
+// twelve consumer warps have released it (one "empty" mbarrier per slot), so the consumers drift up to two stages
+// apart instead of meeting at a CTA barrier every 8 k-steps.
 // Partial blocks per row chunk are folded in chunk order by syrk_reduce_kernel, which also mirrors the result to
 // the full symmetric matrix.  w_r = dvar_r (which = 0) or dvar_r * [clamped row] (which = 1, skipped unless some
 // row was clamped).  Group 0 also accumulates b = sum_r dmu_r t_r.
 // ---------------------------------------------------------------------------------------------------
-constexpr int SY_KB = 32, SY_WARPS = 12, SY_THREADS = SY_WARPS * 32, SY_STAGES = 3;
+constexpr int SY_KB = 32, SY_WARPS = 12, SY_STAGES = 3;     // SY_WARPS consumer warps (one 32 x 32 block each)
+constexpr int SY_CONS_THREADS = SY_WARPS * 32, SY_THREADS = SY_CONS_THREADS + 32;      // + one producer warp
 
 __host__ __device__ inline size_t syrk_stage_doubles(int MP) { return (size_t)SY_KB * (MP + 4) + 3 * SY_KB; }
 // b = sum_r dmu_r t_r rides along: every group of CTAs takes an equal share of the MP columns, a thread one column and
@@ -1645,14 +1662,16 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
   if (which == 1 && (clamp_count == nullptr || *clamp_count == 0u)) return;
   extern __shared__ __align__(16) double sy_sh[];
   __shared__ unsigned long long full[SY_STAGES];     // mbarriers: stage s % SY_STAGES has landed
+  __shared__ unsigned long long empty[SY_STAGES];    // mbarriers: every consumer warp is done with the slot
   const int ld = MP + 4;
   const size_t stage = syrk_stage_doubles(MP);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int nblk = syrk_nblocks(MP);
   const int group = blockIdx.x, chunk = blockIdx.y;
+  const bool producer = warp == SY_WARPS;
   const int q = group * SY_WARPS + warp;
-  const bool active = q < nblk;
+  const bool active = !producer && q < nblk;
   int bi = 0, bj = 0;
   if (active) { int rem = q; while (rem > bi) { rem -= bi + 1; ++bi; } bj = rem; }
   const long long rows_per = ((R + nchunk - 1) / nchunk + SY_KB - 1) / SY_KB * SY_KB;
@@ -1661,9 +1680,9 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
   const int nst = rend > rbeg ? (int)((rend - rbeg + SY_KB - 1) / SY_KB) : 0;
   const bool do_alpha = which == 0 && part_alpha != nullptr && dmu != nullptr;
   const int acols = (MP + (int)gridDim.x - 1) / (int)gridDim.x;                 // columns of b per group
-  const int aparts = acols * 4 <= SY_THREADS ? 4 : (acols * 2 <= SY_THREADS ? 2 : 1);
+  const int aparts = acols * 4 <= SY_CONS_THREADS ? 4 : (acols * 2 <= SY_CONS_THREADS ? 2 : 1);
   const int apart = tid / acols, acol = group * acols + tid % acols;
-  const bool alpha_thread = do_alpha && apart < aparts && acol < MP && acol < (group + 1) * acols;
+  const bool alpha_thread = do_alpha && !producer && apart < aparts && acol < MP;
   const int ak0 = apart * (SY_KB / aparts), ak1 = ak0 + SY_KB / aparts;
   const unsigned row_bytes = (unsigned)MP * sizeof(double);
   // the three per-row arrays travel as 256-byte bulk copies when they are 16-byte aligned (always, for fresh
@@ -1671,12 +1690,12 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
   const bool vec_ok = ((((uintptr_t)dvar) | ((uintptr_t)dmu) | ((uintptr_t)craw)) & 15) == 0;
 
   if (tid == 0) {
-    for (int s = 0; s < SY_STAGES; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < SY_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SY_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // warp 0 fills a stage: one 2 KB bulk copy per row of T (the TMA engine computes no per-element addresses: the
+  // the producer warp fills a stage: one 2 KB bulk copy per row of T (the TMA engine computes no per-element addresses: the
   // per-thread 16-byte cp.async loop of the first version spent 14 % of the kernel's samples on index arithmetic,
   // profiles/r01r_*), completion on the stage's mbarrier
   auto issue = [&](int s) {
@@ -1720,8 +1739,13 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
     for (int y = 0; y < 4; ++y) { acc[x][y][0] = 0.0; acc[x][y][1] = 0.0; }
   double al[4] = {0.0, 0.0, 0.0, 0.0};
 
-  if (warp == 0)
-    for (int s = 0; s < SY_STAGES && s < nst; ++s) issue(s);
+  if (producer) {
+    for (int s = 0; s < nst; ++s) {
+      if (s >= SY_STAGES) mbar_wait(&empty[s % SY_STAGES], (unsigned)(s / SY_STAGES - 1) & 1u);
+      issue(s);
+    }
+    return;
+  }
   for (int it = 0; it < nst; ++it) {
     const int slot = it % SY_STAGES;
     mbar_wait(&full[slot], (unsigned)(it / SY_STAGES) & 1u);
@@ -1751,8 +1775,8 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
 #pragma unroll
         for (int c = 0; c < 4; ++c) al[c] = fma(ws[SY_KB + k + c], Ts[(size_t)(k + c) * ld + acol], al[c]);
     }
-    __syncthreads();   // everyone is done with this slot: refill it with the stage SY_STAGES ahead
-    if (warp == 0 && it + SY_STAGES < nst) issue(it + SY_STAGES);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);      // this warp is done with the slot
   }
   if (active) {
     double* out = part + ((size_t)chunk * nblk + q) * 1024;
@@ -1765,7 +1789,7 @@ syrk_kernel(const double* __restrict__ T, const double* __restrict__ dvar, const
   }
   if (do_alpha) {       // slices a thread count does not reach stay zero
     if (alpha_thread) part_alpha[((size_t)chunk * SY_ALPHA_PARTS + apart) * MP + acol] = (al[0] + al[1]) + (al[2] + al[3]);
-    for (int idx = tid; idx < (SY_ALPHA_PARTS - aparts) * acols; idx += SY_THREADS) {
+    for (int idx = tid; idx < (SY_ALPHA_PARTS - aparts) * acols; idx += SY_CONS_THREADS) {
       const int pz = aparts + idx / acols, cz = group * acols + idx % acols;
       if (cz < MP) part_alpha[((size_t)chunk * SY_ALPHA_PARTS + pz) * MP + cz] = 0.0;
     }

@@ -109,7 +109,8 @@ def test_fused_step_matches_oracle_and_composable(L, S, B, M, freeze):
             a, b = r * B // nsh, (r + 1) * B // nsh
             e = [None] + [t[a * S:b * S] for t in eps_d[1:]]
             step(xb[a:b], yb[a:b], fb[a:b], eps=e, num_samples=S)
-            acc += step.flat.flat
+            # (per parameter: the flat buffer leads with the d L_q blocks, not in named_parameters order)
+            acc += torch.cat([p.grad.reshape(-1) for n, p in model.named_parameters() if p.requires_grad])
         # every shard carries the KL term scaled by its own B_r / N: they add up to the full step's B / N
         # (the SYRK partials fold in another order per partition: ~1e-16 sqrt(rows) there, times cond through
         # dP = W^T N W; an indexing slip in the multi-tile pipelines is an O(1) error)
