@@ -1,5 +1,6 @@
 // extern "C" entry points of libmobocmf_b200.so (declared in include/mobocmf_b200.h) and the host-side kernel
 // sequences behind them.
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include "../../include/mobocmf_b200.h"
@@ -439,8 +440,13 @@ void mobo_step_ctx_destroy(void* ctx) {
 
 static bool g_side_stream_on = true;
 // SMs the backward product kernel (one persistent CTA per SM, all of its registers and shared memory) leaves to the
-// side stream's operator-chain backward; measured on C4: 0 -> 2.84 ms / step, 4 -> 2.72, 8 -> 2.71, 16 -> 2.75
-constexpr int kSideStreamSMs = 8;
+// side stream's operator-chain backward; measured on C4 (ms / step): round 1: 0 -> 2.84, 4 -> 2.72, 8 -> 2.71, 16 -> 2.75;
+// round-2 kernels: 0 -> 2.51, 4 -> 2.41, 8 -> 2.44, 12 -> 2.45, 16 -> 2.45
+constexpr int kSideStreamSMs = 4;
+static int side_stream_sms() {      // development override: MOBO_SIDE_SMS=n
+  static const int n = getenv("MOBO_SIDE_SMS") ? atoi(getenv("MOBO_SIDE_SMS")) : kSideStreamSMs;
+  return n;
+}
 void mobo_step_side_stream(int on) { g_side_stream_on = on != 0; }
 
 size_t mobo_elbo_step_workspace_doubles(int L, int d, int M, int S, long long B) {
@@ -544,7 +550,7 @@ int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
     fill_row_bwd_args(a, ws + y.dmu[l], ws + y.dvar[l], ws + y.craw[l], ws + y.Ts[l], ws + y.Us[l], 1, ws + y.df[l],
                       nullptr);
     a.clamp_count = clamp + l;
-    a.sm_reserve = fork ? kSideStreamSMs : 0;
+    a.sm_reserve = fork ? side_stream_sms() : 0;
     MOBO_TRY(rows_bwd_main(a, kinds[l], d, M, R, ws + y.rows_work, ws + y.rows_work + mobo_rows_save_doubles(M, R),
                            ws + y.dtheta_rows[l], l == 0 ? nullptr : ws + y.dzf_rows[l], st));
   }

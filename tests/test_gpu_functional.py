@@ -130,3 +130,51 @@ def test_forward_backward_matches_oracle(M, d, R, L, ls):
         keys = param_keys(sd)
         adjudicate_state(sd, O.NOISE_LOWER, noise_upper, -elbo_c.detach(), {k: -sdc[k].grad for k in keys},
                          -elbo_o.detach(), {k: -sdo[k].grad for k in keys}, L, x, y, fid, eps, num_data, 1)
+
+
+@pytest.mark.parametrize("M,d,n,S,training", [(256, 6, 37, 64, True), (200, 3, 101, 25, False), (75, 2, 9, 11, True),
+                                                (16, 1, 5, 40, True)])
+def test_sample_tiled_rows_kernel_equals_generic_kernel(M, d, n, S, training):
+    """Rows that are S MC samples of n points (xrep = S >= 11) run in the warp-specialised forward kernel
+    (row_fwd_ws_kernel: product / build / finish warps); the same rows with x tiled explicitly (xrep = 1) run in the
+    generic two-CTA kernel.  Same arithmetic per element, different summation order of the row sums: mean, variance and
+    every gradient must agree to rounding, at ragged sizes (last tile partial, MP < 256, tiles spanning 2 - 3 points),
+    and a second launch must reproduce the first bit for bit (no race in the barrier hand-overs)."""
+    from mobocmf_b200 import functional as F
+    L = 2
+    sd, _ = random_state(M, d, L, seed=7, ls=0.3)
+    sd = clone_state(sd, device="cuda:0")
+    th = thetas(sd, L)
+    Zx = sd["hidden_layer_0.variational_strategy.inducing_points"].contiguous()
+    q = "hidden_layer_%d.variational_strategy._variational_distribution."
+    zf = sd[(q % 0) + "variational_mean"]
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(n, d, generator=g, dtype=torch.float64).cuda()
+    mu0 = torch.randn(n, generator=g, dtype=torch.float64).cuda()
+    var0 = (0.05 + torch.rand(n, generator=g, dtype=torch.float64)).cuda()
+    eps = torch.randn(n * S, generator=g, dtype=torch.float64).cuda()
+    wmu, wvar = torch.randn(n * S, generator=g, dtype=torch.float64).cuda(), torch.randn(n * S, generator=g, dtype=torch.float64).cuda()
+
+    def run(tiled):
+        leaves = [t.detach().clone().requires_grad_(True) for t in (th[1], zf, sd[(q % 1) + "variational_mean"],
+                                                                     sd[(q % 1) + "chol_variational_covar"], mu0, var0)]
+        theta, zf_, m, Lq, mu_p, var_p = leaves
+        ops = F.layer_operators(theta, zf_, m, Lq, Zx, 1)
+        if tiled:     # generic kernel: explicit rows
+            mu, var = F.layer_rows(ops, theta, zf_, Zx, x.repeat_interleave(S, 0).contiguous(),
+                                   mu_prev=mu_p.repeat_interleave(S), var_prev=var_p.repeat_interleave(S), eps=eps, kind=1,
+                                   training=training)
+        else:         # warp-specialised kernel: row r reads x[r // S], mu_prev[r // S]
+            mu, var = F.layer_rows(ops, theta, zf_, Zx, x, mu_prev=mu_p, var_prev=var_p, eps=eps, kind=1, xrep=S, prep=S,
+                                   eps_mod=n * S, R=n * S, training=training)
+        loss = (wmu * mu).sum() + (wvar * var).sum()
+        grads = torch.autograd.grad(loss, leaves)
+        return mu.detach(), var.detach(), [gr.detach() for gr in grads]
+
+    a, b, c = run(False), run(True), run(False)
+    assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    for ga, gc in zip(a[2], c[2]):
+        assert torch.equal(ga, gc)
+    assert relerr(a[0], b[0]) < 1e-12 and relerr(a[1], b[1]) < 1e-12, (relerr(a[0], b[0]), relerr(a[1], b[1]))
+    for k, (ga, gb) in enumerate(zip(a[2], b[2])):
+        assert relerr(ga, gb) < 1e-10, (k, relerr(ga, gb))
