@@ -154,16 +154,12 @@ __device__ __forceinline__ double* tile_ptr(unsigned char* smem) {
 }
 
 constexpr int FWD_NST = 4, BWD_NST = 4;   // A-fragment ring depth (k-steps) of the forward / backward product kernels
+// (frag_group below is written for exactly 4 slots: the fragment of k-step q lives in slot q & 3)
 __host__ __device__ inline size_t tile_bytes(int MP) { return (size_t)TR * (MP + 4) * sizeof(double); }
 __host__ inline size_t row_smem_bytes(int MP) {
   return ((sizeof(RowSmem) + 127) / 128) * 128 + tile_bytes(MP) + (size_t)ROW_WARPS * FWD_NST * 32 * sizeof(double2);
 }
 
-// One warp: acc(2 slabs x 16 rows x 32 cols) += A[slab rows, k-range] * B[k-range, 32 cols].
-// Af: the MP x MP operator in A-fragment order (common.cuh frag_offset; L2-resident), triangular: LOWER uses
-// k < 16(s+1), UPPER uses k >= 16 s.  One 16-byte load per lane and k-step feeds both 8-row halves of the slab and a
-// warp's load is 512 contiguous bytes (4 L1 wavefronts; the row-major form cost 16 for the same data).
-// Bs: shared, Bs[col][k] with leading dimension ldb (ldb % 16 == 4 -> conflict-free fragment loads).
 // 16-byte asynchronous global -> shared copy (L2 only) and its group bookkeeping.  The "memory" clobbers keep the
 // compiler from moving shared-memory reads across the wait.
 __device__ __forceinline__ void cp_async16_cg(void* smem, const void* gmem) {
@@ -173,83 +169,6 @@ __device__ __forceinline__ void cp_async16_cg(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// One warp: acc(2 slabs x 16 rows x 32 cols) += A[slab rows, k-range] * B[k-range, 32 cols].
-// Af: the MP x MP operator in A-fragment order (common.cuh frag_offset; L2-resident), triangular: LOWER uses
-// k < 16(s+1), UPPER uses k >= 16 s.  The fragments come from L2 (several hundred cycles, the top stall of the
-// register-loaded version: ncu long_scoreboard, profiles/r01r_*): each lane streams ITS 16-byte fragment of every
-// k-step through a private slot ring in shared memory with cp.async, NST - 1 k-steps (8 DMMAs each) ahead of its
-// use.  A lane only ever reads the slots it wrote itself, so cp.async.wait_group is the only synchronisation.
-// ring: this warp's NST x 32 double2 slots.
-// Bs: shared, Bs[col][k] with leading dimension ldb (ldb % 16 == 4 -> conflict-free fragment loads).
-template <bool UPPER, int NST, bool KSPLIT = false>
-__device__ __forceinline__ void slab_gemm(double (&acc)[2][2][4][2], const double* __restrict__ Af, int MP,
-                                          const double* Bs, int ldb, int sA, int sB, int half, int lane,
-                                          double2* ring) {
-  static_assert(NST == 4 || NST == 8, "ring depth");
-  const int g = lane >> 2, t = lane & 3;
-  double2* slot = ring + lane;
-  const double* b0 = Bs + (size_t)(32 * half + g) * ldb + t;
-  const size_t ct_stride = (size_t)8 * ldb;
-#pragma unroll
-  for (int sl = 0; sl < 2; ++sl) {
-    const int s = sl == 0 ? sA : sB;
-    const int kbeg = UPPER ? 16 * s : 0;
-    const int nq = (UPPER ? MP - 16 * s : 16 * (s + 1)) >> 2;      // k-steps of 4; a multiple of 4
-    // reads up to NST - 1 fragments past the slab's k-range: still inside the operator buffer (the fragment blocks are
-    // followed by at least 6 MP + 144 doubles, common.cuh), never used
-    const double2* ap = reinterpret_cast<const double2*>(Af) + ((size_t)s * (MP >> 2) + (kbeg >> 2)) * 32 + lane;
-    const double* bp = b0 + kbeg;
-    // KSPLIT: odd k-steps accumulate into a second register set, so consecutive k-steps of a warp are independent
-    // (DMMA latency ~140 cycles = 9 DMMA issue slots; needed when only two warps share a scheduler)
-    double acc2[KSPLIT ? 2 : 1][KSPLIT ? 4 : 1][2];
-    if (KSPLIT) {
-#pragma unroll
-      for (int ib = 0; ib < 2; ++ib)
-#pragma unroll
-        for (int ct = 0; ct < 4; ++ct) { acc2[KSPLIT ? ib : 0][KSPLIT ? ct : 0][0] = 0.0; acc2[KSPLIT ? ib : 0][KSPLIT ? ct : 0][1] = 0.0; }
-    }
-#pragma unroll
-    for (int j = 0; j < NST - 1; ++j) {
-      cp_async16_cg(slot + j * 32, ap + j * 32);
-      cp_async_commit_group();
-    }
-    ap += (NST - 1) * 32;
-    for (int q0 = 0; q0 < nq; q0 += 4) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // slot of k-step q + NST - 1 == slot of k-step q - 1, whose fragment this lane's DMMAs have already consumed
-        cp_async16_cg(slot + ((j + NST - 1) & (NST - 1)) * 32, ap + j * 32);
-        cp_async_commit_group();
-        cp_async_wait_group<NST - 1>();
-        const double2 av = slot[(j & (NST - 1)) * 32];
-#pragma unroll
-        for (int ct = 0; ct < 4; ++ct) {
-          const double b = bp[ct * ct_stride + 4 * j];
-          if (KSPLIT && (j & 1)) {
-            dmma884(acc2[0][KSPLIT ? ct : 0][0], acc2[0][KSPLIT ? ct : 0][1], av.x, b);
-            dmma884(acc2[KSPLIT ? 1 : 0][KSPLIT ? ct : 0][0], acc2[KSPLIT ? 1 : 0][KSPLIT ? ct : 0][1], av.y, b);
-          } else {
-            dmma884(acc[sl][0][ct][0], acc[sl][0][ct][1], av.x, b);
-            dmma884(acc[sl][1][ct][0], acc[sl][1][ct][1], av.y, b);
-          }
-        }
-      }
-      ap += 4 * 32;
-      bp += 16;
-    }
-    cp_async_wait_group<0>();   // the look-ahead copies: drain before the next slab reuses the slots
-    if (KSPLIT) {
-#pragma unroll
-      for (int ib = 0; ib < 2; ++ib)
-#pragma unroll
-        for (int ct = 0; ct < 4; ++ct) {
-          acc[sl][ib][ct][0] += acc2[KSPLIT ? ib : 0][KSPLIT ? ct : 0][0];
-          acc[sl][ib][ct][1] += acc2[KSPLIT ? ib : 0][KSPLIT ? ct : 0][1];
-        }
-    }
-  }
-}
 
 __device__ __forceinline__ void zero_acc(double (&acc)[2][2][4][2]) {
 #pragma unroll
@@ -1362,12 +1281,15 @@ __device__ __forceinline__ void kgrad_tile_d(const RowArgs& a, SM& sm, const dou
 // are accumulated by syrk_kernel from the saved T and consumed by the operator backward (matrix_ops.cu).
 // ---------------------------------------------------------------------------------------------------
 struct BwdSmem {
-  double dmu[TR], dvar[TR], mask[TR];
-  unsigned long long bar;     // mbarrier: the staged u / t rows of the next tile have landed
+  double dmu[2][TR], dvar[2][TR], mask[2][TR];      // per-row scalars, double-buffered by the producer warp
+  unsigned long long bar;     // mbarrier: the staged u / t rows (and the row scalars) of the next tile have landed
 };
+constexpr int BWD_THREADS = ROW_THREADS + 32;       // 8 product warps + the producer warp
+__device__ __forceinline__ void bar_sync_bwd() { asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory"); }
+constexpr size_t BWD_HEAD = 2048;
 // [BwdSmem | X tile | U stage | T stage | A-fragment rings]; tiles are [TR][MP + 4]
 __host__ __device__ inline size_t bwd_smem_bytes(int MP) {
-  return 1024 + 3 * tile_bytes(MP) + (size_t)ROW_WARPS * BWD_NST * 32 * sizeof(double2);
+  return BWD_HEAD + 3 * tile_bytes(MP) + (size_t)ROW_WARPS * BWD_NST * 32 * sizeof(double2);
 }
 
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
@@ -1403,20 +1325,24 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned 
 // while tile i's second product runs, and dk leaves straight from the accumulators, so no warp ever waits on HBM
 // (with the synchronous loads of the first version the memory phases cost 13 us of every 32 us tile and two CTAs per
 // SM did not hide them: profiles/r01z_*).  Per tile: y = H u (B operand read in place from the u stage), dt from y and
-// the t stage into the X tile, barrier, prefetch of the next tile, dk = W^T dt.
-__global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_gemm_kernel(const __grid_constant__ RowArgs a) {
+// the t stage into the X tile, barrier, dk = W^T dt.  A ninth warp is the PRODUCER: it issues the bulk copies and
+// loads the row scalars of the next tile.  (When warp 0 did that on top of its products, the 64 bulk-copy instructions
+// cost it 5.5k cycles per tile, it finished its second product that much later, and the other seven warps waited for
+// it at the next tile's barrier: 12 % of the kernel, tools/row_bench -DROW_TIMING.)
+__global__ void __launch_bounds__(BWD_THREADS, 1) row_bwd_gemm_kernel(const __grid_constant__ RowArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
-  static_assert(sizeof(BwdSmem) <= 1024, "BwdSmem");
+  static_assert(sizeof(BwdSmem) <= BWD_HEAD, "BwdSmem");
   const int MP = a.MP, ldb = MP + 4;
-  double* X = reinterpret_cast<double*>(smem_raw + 1024);
-  double* BU = reinterpret_cast<double*>(smem_raw + 1024 + tile_bytes(MP));
-  double* BT = reinterpret_cast<double*>(smem_raw + 1024 + 2 * tile_bytes(MP));
+  double* X = reinterpret_cast<double*>(smem_raw + BWD_HEAD);
+  double* BU = reinterpret_cast<double*>(smem_raw + BWD_HEAD + tile_bytes(MP));
+  double* BT = reinterpret_cast<double*>(smem_raw + BWD_HEAD + 2 * tile_bytes(MP));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double2* ring = reinterpret_cast<double2*>(smem_raw + 1024 + 3 * tile_bytes(MP)) + warp * BWD_NST * 32;
+  const bool producer = warp == ROW_WARPS;
+  double2* ring = reinterpret_cast<double2*>(smem_raw + BWD_HEAD + 3 * tile_bytes(MP)) + (producer ? 0 : warp) * BWD_NST * 32;
   const int half = warp % NHALF, p = warp / NHALF;
   const int npairs = MP / 32, ns = MP / 16;
-  const bool active = p < npairs;
+  const bool active = !producer && p < npairs;
   const int sA = p, sB = ns - 1 - p;
   const int g = lane >> 2, t = lane & 3;
   const double* WT = a.ops + ops_block(MP, OPS_WTF);
@@ -1425,40 +1351,45 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_gemm_kernel(const __gr
   const long long ntiles = (a.R + TR - 1) / TR;
   const unsigned row_bytes = (unsigned)MP * sizeof(double);
 
+  RT_DECL
   if (tid == 0) {
     mbar_init(&sm.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // warp 0: one bulk copy per row and array; invalid rows of a ragged last tile keep stale (finite or not, never
-  // stored: every column of the products depends on its own row only) data
-  auto stage_tile = [&](long long tile) {
-    const long long row0 = tile * TR;
-    const int nvalid = (int)min((long long)TR, a.R - row0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the stages -> async writes
-    if (lane == 0) mbar_expect_tx(&sm.bar, 2u * (unsigned)nvalid * row_bytes);
-    __syncwarp();
-    if (lane < nvalid) {
-      bulk_g2s(BU + (size_t)lane * ldb, a.Usave + (size_t)(row0 + lane) * MP, row_bytes, &sm.bar);
-      bulk_g2s(BT + (size_t)lane * ldb, a.Tsave + (size_t)(row0 + lane) * MP, row_bytes, &sm.bar);
+  if (producer) {
+    // row scalars of tile number `it` of this CTA into buffer it & 1, then one bulk copy per row and array; invalid
+    // rows of a ragged last tile keep stale (finite or not, never stored: every column of the products depends on its
+    // own row only) data.  The mbarrier arrive (release) after the generic writes makes them visible to the waiters.
+    auto stage_tile = [&](long long tile, int buf) {
+      const long long row0 = tile * TR;
+      const int nvalid = (int)min((long long)TR, a.R - row0);
+      const long long row = row0 + lane;
+      const bool ok = row < a.R;
+      sm.dmu[buf][lane] = ok ? a.dmu[row] : 0.0;
+      sm.dvar[buf][lane] = ok ? a.dvar[row] : 0.0;
+      sm.mask[buf][lane] = (ok && a.training && a.craw) ? (a.craw[row] >= 0.0 ? 1.0 : 0.0) : 1.0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the stages -> async writes
+      __syncwarp();
+      if (lane == 0) mbar_expect_tx(&sm.bar, 2u * (unsigned)nvalid * row_bytes);
+      __syncwarp();
+      if (lane < nvalid) {
+        bulk_g2s(BU + (size_t)lane * ldb, a.Usave + (size_t)(row0 + lane) * MP, row_bytes, &sm.bar);
+        bulk_g2s(BT + (size_t)lane * ldb, a.Tsave + (size_t)(row0 + lane) * MP, row_bytes, &sm.bar);
+      }
+    };
+    long long tile = blockIdx.x;
+    if (tile < ntiles) stage_tile(tile, 0);
+    int it = 0;
+    for (; tile < ntiles; tile += gridDim.x, ++it) {
+      __syncthreads();   // this tile's dt is complete: the u / t stages are free
+      const long long next = tile + gridDim.x;
+      if (next < ntiles) stage_tile(next, (it + 1) & 1);
     }
-  };
-  // per-row scalars of a tile, prefetched into registers of the first TR threads one tile ahead
-  double pf_dmu = 0.0, pf_dvar = 0.0, pf_mask = 1.0;
-  auto prefetch_rows = [&](long long tile) {
-    const long long row = tile * TR + tid;
-    const bool ok = row < a.R;
-    pf_dmu = ok ? a.dmu[row] : 0.0;
-    pf_dvar = ok ? a.dvar[row] : 0.0;
-    pf_mask = (ok && a.training && a.craw) ? (a.craw[row] >= 0.0 ? 1.0 : 0.0) : 1.0;
-  };
-
-  long long tile = blockIdx.x;
-  if (tile < ntiles) {
-    if (warp == 0) stage_tile(tile);
-    if (tid < TR) prefetch_rows(tile);
+    return;
   }
+
   // A-fragment stream as in the forward kernel (frag_segment): four segments per tile (H slab A, H slab B, W^T slab A,
   // W^T slab B), each priming the ring for the next, so that no segment starts with an L2 round trip (4 per tile in the
   // first version, ~6 % of a tile), and the half-zero diagonal blocks skip their zero DMMAs
@@ -1468,19 +1399,23 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_gemm_kernel(const __gr
     for (int j = 0; j < 3; ++j) { cp_async16_cg(ring + lane + j * 32, first + j * 32); cp_async_commit_group(); }
   }
   unsigned parity = 0;
-  for (; tile < ntiles; tile += gridDim.x) {
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const long long row0 = tile * TR;
     const int nvalid = (int)min((long long)TR, a.R - row0);
-    if (tid < TR) { sm.dmu[tid] = pf_dmu; sm.dvar[tid] = pf_dvar; sm.mask[tid] = pf_mask; }
+    const int sb = it & 1;
+    RT_TICKW(1, 0);
     mbar_wait(&sm.bar, parity);
     parity ^= 1u;
-    __syncthreads();
+    bar_sync_bwd();    // every product warp is done with the previous tile's X
+    RT_TICKW(1, 1);
     double acc[2][2][4][2];
     if (active) {
       // ---- y = H u ----
       zero_acc(acc);
       frag_segment<false>(acc[0], H, MP, BU, ldb, sA, half, lane, ring, frag_start(H, MP, sB, false, lane));
       frag_segment<false>(acc[1], H, MP, BU, ldb, sB, half, lane, ring, frag_start(WT, MP, sA, true, lane));
+      RT_TICKW(1, 2);
       // ---- dt = dmu beta - 2 dvar (mask t - y) ----
 #pragma unroll
       for (int sl = 0; sl < 2; ++sl)
@@ -1494,26 +1429,26 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_bwd_gemm_kernel(const __gr
             for (int e = 0; e < 2; ++e) {
               const int r = 32 * half + 8 * ct + 2 * t + e;
               const double tv = BT[(size_t)r * ldb + i];
-              acc[sl][ib][ct][e] = sm.dmu[r] * bi - 2.0 * sm.dvar[r] * (sm.mask[r] * tv - acc[sl][ib][ct][e]);
+              acc[sl][ib][ct][e] = sm.dmu[sb][r] * bi - 2.0 * sm.dvar[sb][r] * (sm.mask[sb][r] * tv - acc[sl][ib][ct][e]);
             }
         }
       store_acc_to_tile(acc, X, ldb, sA, sB, half, lane);
     }
-    __syncthreads();   // dt complete in X; the u / t stages and the row scalars are free
-    const long long next = tile + gridDim.x;
-    if (next < ntiles) {
-      if (warp == 0) stage_tile(next);
-      if (tid < TR) prefetch_rows(next);
-    }
+    RT_TICKW(1, 3);
+    __syncthreads();   // dt complete in X; the producer may refill the u / t stages
+    RT_TICKW(1, 4);
     // ---- dk = W^T dt, straight from the accumulators to HBM ----
     if (active) {
       zero_acc(acc);
       frag_segment<true>(acc[0], WT, MP, X, ldb, sA, half, lane, ring, frag_start(WT, MP, sB, true, lane));
       frag_segment<true>(acc[1], WT, MP, X, ldb, sB, half, lane, ring, frag_start(H, MP, sA, false, lane));
+      RT_TICKW(1, 6);
       store_acc_rows(acc, a.dk, row0, nvalid, MP, sA, sB, half, lane);
     }
   }
+  RT_TICKW(1, 7);
   cp_async_wait_group<0>();     // the chained look-ahead of the last segment
+  RT_FLUSH(1);
 }
 
 // ---- through the covariance function: 4 warps x RPW rows per tile, 3 CTAs per SM ----
@@ -1914,7 +1849,7 @@ int launch_row_bwd(const RowArgs& a, cudaStream_t st) {
   if (((uintptr_t)a.Tsave | (uintptr_t)a.Usave) & 15) return -2;   // bulk copies need 16-byte aligned rows
   const int grid_b = row_bwd_grid(a.R, a.sm_reserve);
   MOBO_LAUNCH("row_bwd_gemm_kernel", st,
-              row_bwd_gemm_kernel<<<grid_b, ROW_THREADS, bwd_smem_bytes(a.MP), st>>>(a));
+              row_bwd_gemm_kernel<<<grid_b, BWD_THREADS, bwd_smem_bytes(a.MP), st>>>(a));
   const int grid = kgrad_grid(a.R);
   const size_t smem = kg_smem_bytes();
   if (a.want_param_grads && a.want_x_grads) {

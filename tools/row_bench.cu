@@ -110,6 +110,16 @@ int main(int argc, char** argv) {
     }
   }
 #ifdef ROW_TIMING
+  {   // backward product kernel: phases of thread 0 (rows_bwd above was the last launch of it)
+    cudaDeviceSynchronize();
+    static unsigned long long tb[3][512][16];
+    cudaMemcpyFromSymbol(tb, mobo::row_times, sizeof(tb));
+    const char* nb[8] = {"(top: row scalars -> smem)", "WAIT: staged u / t, sync", "y = H u (warp 0)", "dt, dt -> tile", "sync", "stage next tile (warp 0)", "dk = W^T dt (warp 0)", "dk stores"};
+    double tt = 0, ss[8] = {0};
+    for (int b = 0; b < 148; ++b) for (int k = 0; k < 8; ++k) { ss[k] += (double)tb[1][b][k]; tt += (double)tb[1][b][k]; }
+    printf("backward product kernel, cycles of thread 0 summed over the CTAs: share per phase\n");
+    for (int k = 0; k < 8; ++k) printf("  %-30s %6.2f %%   %9.0f cycles per CTA\n", nb[k], 100.0 * ss[k] / tt, ss[k] / 148);
+  }
   {
     mobo_layer_rows_fwd(1, d, M, Zx, zf, theta, ops, x, S, mu_prev, var_prev, S, eps, R, nullptr, R, 1, mu, var, craw, clamp,
                         Ts, Us, nullptr);
