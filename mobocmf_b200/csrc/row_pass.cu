@@ -985,19 +985,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) row_fwd_ws_kernel(const __grid_
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
   };
-  // bulk (TMA engine) copies of the tile's valid rows to dst[R][MP], issued by the role's warp 0, which also waits
-  // until the engine has read them (the buffer is rewritten next)
+  // bulk (TMA engine) copies of the tile's valid rows to dst[R][MP]: every finish warp issues a quarter of them (a
+  // bulk-copy instruction costs its warp ~80 cycles; one warp issuing all 32 fell 2.7k cycles behind the others) and
+  // waits until the engine has read its own (the buffer is rewritten next)
+  constexpr int ROWS_PER_FIN_WARP = TR / WS_FIN_WARPS;
   auto bulk_rows_out = [&](double* dst, const double* Ks, unsigned row0, int nvalid) {
-    if (warp == 0) {
-      if (lane < nvalid)
+    if (lane < ROWS_PER_FIN_WARP) {
+      const int r = warp * ROWS_PER_FIN_WARP + lane;
+      if (r < nvalid)
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
-                         dst + (size_t)(row0 + (unsigned)lane) * MP),
-                     "r"((unsigned)__cvta_generic_to_shared(Ks + (size_t)lane * ldb)),
+                         dst + (size_t)(row0 + (unsigned)r) * MP),
+                     "r"((unsigned)__cvta_generic_to_shared(Ks + (size_t)r * ldb)),
                      "r"((unsigned)(MP * sizeof(double))) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   };
-  auto bulk_wait_read = [&]() { if (warp == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); };
+  auto bulk_wait_read = [&]() { if (lane < ROWS_PER_FIN_WARP) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); };
   for (unsigned i = 0; i < n; ++i) {
     const int b = i & 1;
     const double* Ks = tile_buf(b);
