@@ -283,8 +283,10 @@ static int rows_bwd_stats(int MP, long long R, int training, const double* Tsave
 }
 
 // product kernel + covariance-gradient kernel + the fixed-order reduction of the latter's per-CTA partials
+// the fold of the covariance-gradient kernel's per-CTA partials (latency-bound: a few hundred dependent loads per
+// output) may run on another stream `rs` once `ev` (recorded on `st` behind the kernel) has fired
 static int rows_bwd_main(RowArgs& a, int kind, int d, int M, long long R, double* dk, double* part, double* dtheta,
-                         double* dzf, cudaStream_t st) {
+                         double* dzf, cudaStream_t st, cudaStream_t rs = nullptr, cudaEvent_t ev = nullptr) {
   const int MP = a.MP;
   const int grid = kgrad_grid(R);
   a.dk = dk;
@@ -292,8 +294,13 @@ static int rows_bwd_main(RowArgs& a, int kind, int d, int M, long long R, double
   a.part_zf = part + (size_t)grid * MAX_THETA;
   MOBO_TRY(launch_row_bwd(a, st));
   if (a.want_param_grads && dtheta) {
-    MOBO_TRY(launch_reduce_partials(a.part_theta, grid, theta_size(kind, d), MAX_THETA, dtheta, 0, st));
-    if (kind == 1 && dzf) MOBO_TRY(launch_reduce_partials(a.part_zf, grid, M, MP, dzf, 0, st));
+    cudaStream_t r = st;
+    if (rs && ev) {
+      if (cudaEventRecord(ev, st) != cudaSuccess || cudaStreamWaitEvent(rs, ev, 0) != cudaSuccess) return -1;
+      r = rs;
+    }
+    MOBO_TRY(launch_reduce_partials(a.part_theta, grid, theta_size(kind, d), MAX_THETA, dtheta, 0, r));
+    if (kind == 1 && dzf) MOBO_TRY(launch_reduce_partials(a.part_zf, grid, M, MP, dzf, 0, r));
   }
   return 0;
 }
@@ -342,7 +349,8 @@ struct StepLayout {
       craw[ST_MAX_LAYERS], dmu[ST_MAX_LAYERS], dvar[ST_MAX_LAYERS], df[ST_MAX_LAYERS], Ts[ST_MAX_LAYERS],
       Us[ST_MAX_LAYERS], dtheta_rows[ST_MAX_LAYERS], dtheta_pre[ST_MAX_LAYERS], dzf_rows[ST_MAX_LAYERS],
       dzf_pre[ST_MAX_LAYERS], dm_pre[ST_MAX_LAYERS], dLq_tmp[ST_MAX_LAYERS], pre_work[ST_MAX_LAYERS],
-      ell_part[ST_MAX_LAYERS], stats0[ST_MAX_LAYERS], stats1[ST_MAX_LAYERS], stats_alpha[ST_MAX_LAYERS];
+      ell_part[ST_MAX_LAYERS], stats0[ST_MAX_LAYERS], stats1[ST_MAX_LAYERS], stats_alpha[ST_MAX_LAYERS],
+      kg_part[ST_MAX_LAYERS];
   long long R[ST_MAX_LAYERS];
   int ell_blocks[ST_MAX_LAYERS];
   size_t noise, clamp, rows_work, total;
@@ -379,6 +387,8 @@ StepLayout step_layout(int L, int d, int M, int S, long long B) {
     y.stats0[l] = take(syrk_part_doubles(MP, R));
     y.stats1[l] = take(syrk_part_doubles(MP, R));
     y.stats_alpha[l] = take(syrk_alpha_doubles(MP, syrk_nchunk(MP, R)) + 64);
+    // per-CTA partials of the covariance-gradient kernel, per layer: their fold runs on the side stream too
+    y.kg_part[l] = take((size_t)256 * KG_CTAS_PER_SM * (MAX_THETA + MP) + 64);
   }
   y.rows_work = take(rows_work);
   y.total = off;
@@ -398,13 +408,15 @@ namespace {
 struct SideCtx {
   int device = -1; cudaStream_t s = nullptr; cudaEvent_t fork[ST_MAX_LAYERS]; cudaEvent_t join = nullptr;
   cudaEvent_t done[ST_MAX_LAYERS];      // layer l's operator-chain backward (its d L_q, d m, d theta shares) is complete
+  cudaEvent_t kg[ST_MAX_LAYERS];        // layer l's covariance-gradient kernel is complete (its partials may be folded)
 };
 bool side_ctx_init(SideCtx& c) {
   if (cudaGetDevice(&c.device) != cudaSuccess) return false;
   if (cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking) != cudaSuccess) return false;
   for (int i = 0; i < ST_MAX_LAYERS; ++i)
     if (cudaEventCreateWithFlags(&c.fork[i], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c.done[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        cudaEventCreateWithFlags(&c.done[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.kg[i], cudaEventDisableTiming) != cudaSuccess) return false;
   return cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) == cudaSuccess;
 }
 SideCtx* default_side_ctx() {
@@ -433,7 +445,7 @@ void mobo_step_ctx_destroy(void* ctx) {
   SideCtx* c = static_cast<SideCtx*>(ctx);
   if (!c) return;
   if (c->s) cudaStreamDestroy(c->s);
-  for (int i = 0; i < ST_MAX_LAYERS; ++i) { if (c->fork[i]) cudaEventDestroy(c->fork[i]); if (c->done[i]) cudaEventDestroy(c->done[i]); }
+  for (int i = 0; i < ST_MAX_LAYERS; ++i) { if (c->fork[i]) cudaEventDestroy(c->fork[i]); if (c->done[i]) cudaEventDestroy(c->done[i]); if (c->kg[i]) cudaEventDestroy(c->kg[i]); }
   if (c->join) cudaEventDestroy(c->join);
   delete c;
 }
@@ -551,8 +563,8 @@ int mobo_elbo_step(const mobo_step_desc* D, void* stream) {
                       nullptr);
     a.clamp_count = clamp + l;
     a.sm_reserve = fork ? side_stream_sms() : 0;
-    MOBO_TRY(rows_bwd_main(a, kinds[l], d, M, R, ws + y.rows_work, ws + y.rows_work + mobo_rows_save_doubles(M, R),
-                           ws + y.dtheta_rows[l], l == 0 ? nullptr : ws + y.dzf_rows[l], st));
+    MOBO_TRY(rows_bwd_main(a, kinds[l], d, M, R, ws + y.rows_work, ws + y.kg_part[l], ws + y.dtheta_rows[l],
+                           l == 0 ? nullptr : ws + y.dzf_rows[l], st, fork ? ss : nullptr, fork ? sc.kg[l] : nullptr));
   }
   // 5. join: the gradient assembly needs both streams' results
   if (fork && (cudaEventRecord(sc.join, ss) != cudaSuccess || cudaStreamWaitEvent(st, sc.join, 0) != cudaSuccess)) return -1;
