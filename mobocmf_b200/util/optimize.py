@@ -22,7 +22,7 @@ class GraphedValueAndGrad(object):
     """X (n, 1, d) -> (-sum fn(X), d(-sum) / dX, fn(X)) replayed from a CUDA graph.  ``fn`` must be capturable: no host
     synchronisation, shapes fixed by X's (the MFDGP acquisition chain is, once its eval-mode operators are cached)."""
 
-    def __init__(self, fn, n, d, device, warmup=2):
+    def __init__(self, fn, n, d, device, warmup=1):
         self.n, self.d = n, d
         self.X = torch.zeros(n, 1, d, dtype=torch.float64, device=device, requires_grad=True)
         self.X._mobo_not_z = True        # never the inducing inputs: keeps the (synchronising) shortcut test out of capture
