@@ -106,6 +106,32 @@ def test_optimize_acqf_stand_in_finds_the_maximum_on_cpu():
     assert x.shape == (1, 2) and torch.allclose(x[0], target, atol=1e-5) and float(v) > -1e-9
 
 
+def test_optimize_acqf_multi_equals_separate_runs_on_cpu():
+    """get_nextpoint_coupled's loop over the fidelities (acquisition_functions/JESMOC_MFDGP.py:151-168) as ONE
+    multi-start L-BFGS-B run: the joint objective is separable, so every function ends at its own maximum."""
+    from mobocmf_b200.util.optimize import optimize_acqf, optimize_acqf_multi
+    targets = [torch.tensor([0.3, 0.7], dtype=torch.double), torch.tensor([0.8, 0.1], dtype=torch.double),
+               torch.tensor([0.5, 0.5], dtype=torch.double)]
+    calls = []
+
+    def make(t, scale):
+        def acq(X):
+            assert X.dim() == 3 and X.shape[1] == 1
+            calls.append(X.shape[0])
+            return scale - scale * ((X[:, 0, :] - t) ** 2).sum(-1)
+        return acq
+    fns = [make(t, s) for t, s in zip(targets, (1.0, 3.0, 0.5))]
+    bounds = torch.tensor([[0.0, 0.0], [1.0, 1.0]], dtype=torch.double)
+    out, info = optimize_acqf_multi(fns, bounds, num_restarts=4, raw_samples=32, options={"maxiter": 60}, seed=1,
+                                    return_info=True)
+    assert len(out) == 3 and info["graph"] is False and info["evaluations"] >= 2
+    for (x, v), t, s in zip(out, targets, (1.0, 3.0, 0.5)):
+        assert x.shape == (1, 2) and torch.allclose(x[0], t, atol=1e-5) and abs(float(v) - s) < 1e-8
+    assert set(calls) == {32, 4}          # raw-sample screening, then the restarts of each function as one slice
+    x1, v1 = optimize_acqf(fns[1], bounds, num_restarts=4, raw_samples=32, options={"maxiter": 60}, seed=1)
+    assert torch.allclose(x1[0], out[1][0][0], atol=1e-5)
+
+
 def test_operator_buffer_layout_mirror_matches_library():
     from mobocmf_b200 import _lib
     from mobocmf_b200.functional import ops_layout, padded_m
