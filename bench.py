@@ -119,6 +119,8 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg = dict(C4)
+    if os.environ.get("MOBO_BENCH_B"):          # development: another minibatch size (not the BASELINE workload)
+        cfg["B"] = int(os.environ["MOBO_BENCH_B"])
     x, y, fid = c4_data(cfg)
     model = build_model(cfg, x, y, fid, dev)
     elbo = VariationalELBOMF(model, cfg["N"], cfg["L"])
